@@ -1,0 +1,363 @@
+// BLS12-381 scalar field (Fr) arithmetic for sm_100a, 8 x 32-bit limbs, Montgomery form R = 2^256.
+//
+// Device replacement for the `BlsScalar` operations on the reference's hot path (reference call
+// sites: src/strategies/scalar.rs:28 `+=`, :33 `square`/`*`, :44 `*`,`+=`; the arithmetic itself
+// is the external crate dusk-bls12_381 0.13, Cargo.toml:12).  The in-memory format equals
+// `BlsScalar` (4 LE u64 Montgomery limbs == 8 LE u32 limbs), so states cross the FFI without
+// conversion, and every public result is fully reduced to [0,p): representations are unique, so
+// results are bit-identical to the reference's.
+//
+// Design (B200 / sm_100a):
+//  * every 32x32->64 product is a PTX `mad.lo.cc.u32` + `madc.hi.cc.u32` pair inside one carry
+//    chain; ptxas fuses each pair into ONE `IMAD.WIDE.U32.X Rd, Pout, Ra, Rb|UR, Rc, Pin` (carry
+//    in a predicate), so the int-multiply pipe sees exactly one op per limb product;
+//  * "even/odd" accumulators: products a[k]*b with k even land on 64-bit columns of `even`
+//    (limb positions 0..8), k odd on columns of `odd` (positions 1..9): no carry ripples;
+//  * word-serial Montgomery reduction interleaved with the products (CIOS), generalised to an
+//    N-term dot product  sum_j c_j*v_j  that is reduced ONCE (lazy reduction of an MDS row);
+//  * special modulus: p[0] = 1 and -p^{-1} mod 2^32 = 0xffffffff, so the Montgomery quotient is
+//    m = -t0 (no multiply) and m*p[0] needs no product: 7 products per reduction step.
+//
+// The same source compiles with g++ -DHADES_HOST_EMUL (tests/host_emul): the PTX chains are then
+// replaced by portable C++ of identical semantics, so the limb-level algorithm is checked against
+// the CPU oracle without a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(HADES_HOST_EMUL)
+#include <assert.h>
+#define HADES_DEV inline
+#define HADES_EMUL 1
+#define HADES_ASSERT(x) assert(x)
+#else
+#define HADES_DEV __device__ __forceinline__
+#define HADES_EMUL 0
+#define HADES_ASSERT(x)
+#endif
+
+namespace hades {
+
+// p = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001 (README.md:35)
+// limb k (0..8) of p << s; every use has compile-time k, s, so these fold to immediates.
+HADES_DEV constexpr uint32_t p_limb(int k) {
+    return k == 0 ? 0x00000001u : k == 1 ? 0xffffffffu : k == 2 ? 0xfffe5bfeu : k == 3 ? 0x53bda402u
+         : k == 4 ? 0x09a1d805u : k == 5 ? 0x3339d808u : k == 6 ? 0x299d7d48u : k == 7 ? 0x73eda753u : 0u;
+}
+HADES_DEV constexpr uint32_t p_shl_limb(int s, int k) {
+    return s == 0 ? p_limb(k) : ((p_limb(k) << s) | (k > 0 ? (p_limb(k - 1) >> (32 - s)) : 0u));
+}
+
+struct Fr {
+    uint32_t l[8];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Chain primitives.  Each is ONE asm statement: the carry flag never lives across statements.
+// ------------------------------------------------------------------------------------------------
+#if HADES_EMUL
+namespace emul {
+// acc (64-bit column k = limbs 2k,2k+1) += a[k]*b, k = k0..3, with carry-in; returns carry-out.
+inline uint64_t chain(uint32_t* acc, const uint32_t* a, int k0, uint32_t b, uint64_t carry) {
+    for (int k = k0; k < 4; k++) {
+        unsigned __int128 t = (unsigned __int128)a[k] * b + (((uint64_t)acc[2 * k + 1] << 32) | acc[2 * k]) + carry;
+        acc[2 * k] = (uint32_t)t;
+        acc[2 * k + 1] = (uint32_t)(t >> 32);
+        carry = (uint64_t)(t >> 64);
+    }
+    return carry;
+}
+inline void top(uint32_t& t, uint64_t carry) {
+    uint64_t s = (uint64_t)t + carry;
+    HADES_ASSERT((s >> 32) == 0);  // the 9th limb only ever holds a few carries
+    t = (uint32_t)s;
+}
+}  // namespace emul
+#endif
+
+// acc[0..7] += {a0,a1,a2,a3}*b on four consecutive 64-bit columns; carry-out added into acc[8].
+HADES_DEV void cmad4(uint32_t (&acc)[9], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#if !HADES_EMUL
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#else
+    const uint32_t a[4] = {a0, a1, a2, a3};
+    emul::top(acc[8], emul::chain(acc, a, 0, b, 0));
+#endif
+}
+
+// Same, preceded by  e0 += x  whose carry enters the chain.  `x` is the limb that falls off the
+// other accumulator in the one-limb right shift; e0 and x share a limb position and acc[0] is
+// the position right above it.
+HADES_DEV void cmad4_shiftin(uint32_t (&acc)[9], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b,
+                             uint32_t& e0, uint32_t x) {
+#if !HADES_EMUL
+    asm("add.cc.u32 %9, %9, %15;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(e0)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b), "r"(x));
+#else
+    uint64_t s = (uint64_t)e0 + x;
+    e0 = (uint32_t)s;
+    const uint32_t a[4] = {a0, a1, a2, a3};
+    emul::top(acc[8], emul::chain(acc, a, 0, b, s >> 32));
+#endif
+}
+
+// Montgomery step on the accumulator that owns limb 0.  With m = -acc[0] mod 2^32:
+//   acc += m * (p0 + p2*2^64 + p4*2^128 + p6*2^192);  p0 = 1 so limb 0 becomes 0 and only its
+//   carry (acc[0] != 0) matters.  3 products.  (The odd limbs p1,p3,p5,p7 go through cmad4.)
+HADES_DEV void redc_even(uint32_t (&acc)[9], uint32_t m) {
+#if !HADES_EMUL
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "madc.lo.cc.u32 %2, %9, 0xfffe5bfe, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, 0xfffe5bfe, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, 0x09a1d805, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, 0x09a1d805, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, 0x299d7d48, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, 0x299d7d48, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(m));
+#else
+    uint64_t s = (uint64_t)acc[0] + m;
+    acc[0] = (uint32_t)s;
+    HADES_ASSERT(acc[0] == 0);
+    s = (uint64_t)acc[1] + (s >> 32);
+    acc[1] = (uint32_t)s;
+    const uint32_t a[4] = {0, p_limb(2), p_limb(4), p_limb(6)};
+    emul::top(acc[8], emul::chain(acc, a, 1, m, s >> 32));
+#endif
+}
+
+// r[0..8] = even + (odd << 32) + x   (x at limb 0); the discarded limb above r[8] must be zero.
+HADES_DEV void merge_even_odd(uint32_t (&r)[9], const uint32_t (&e)[9], const uint32_t (&o)[9], uint32_t x) {
+#if !HADES_EMUL
+    asm("add.cc.u32 %0, %9, %26;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, %17, %25;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8])
+        : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]),
+          "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(x));
+#else
+    uint64_t s = (uint64_t)e[0] + x;
+    r[0] = (uint32_t)s;
+    for (int k = 1; k < 9; k++) {
+        s = (uint64_t)e[k] + o[k - 1] + (s >> 32);
+        r[k] = (uint32_t)s;
+    }
+    HADES_ASSERT((s >> 32) == 0 && o[8] == 0);
+#endif
+}
+
+// (a[0..7], a8 as limb 8) - (p << S) over 9 limbs; difference (low 8 limbs) in d, limb 8 of the
+// difference in d8; returns 1 if the value was below p << S (final borrow).
+template <int S>
+HADES_DEV uint32_t sub_p_shl(uint32_t (&d)[8], uint32_t& d8, const uint32_t (&a)[8], uint32_t a8) {
+    uint32_t below;
+#if !HADES_EMUL
+    uint32_t t8, t9;
+    asm("sub.cc.u32 %0, %10, %19;\n\t"
+        "subc.cc.u32 %1, %11, %20;\n\t"
+        "subc.cc.u32 %2, %12, %21;\n\t"
+        "subc.cc.u32 %3, %13, %22;\n\t"
+        "subc.cc.u32 %4, %14, %23;\n\t"
+        "subc.cc.u32 %5, %15, %24;\n\t"
+        "subc.cc.u32 %6, %16, %25;\n\t"
+        "subc.cc.u32 %7, %17, %26;\n\t"
+        "subc.cc.u32 %8, %18, %27;\n\t"
+        "subc.u32 %9, 0, 0;"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+          "=r"(t8), "=r"(t9)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a8),
+          "r"(p_shl_limb(S, 0)), "r"(p_shl_limb(S, 1)), "r"(p_shl_limb(S, 2)), "r"(p_shl_limb(S, 3)),
+          "r"(p_shl_limb(S, 4)), "r"(p_shl_limb(S, 5)), "r"(p_shl_limb(S, 6)), "r"(p_shl_limb(S, 7)),
+          "r"(p_shl_limb(S, 8)));
+    d8 = t8;
+    below = t9 & 1u;  // 0 - 0 - borrow
+#else
+    uint64_t bw = 0;
+    for (int k = 0; k < 8; k++) {
+        uint64_t t = (uint64_t)a[k] - p_shl_limb(S, k) - bw;
+        d[k] = (uint32_t)t;
+        bw = (t >> 63) & 1;
+    }
+    uint64_t t = (uint64_t)a8 - p_shl_limb(S, 8) - bw;
+    d8 = (uint32_t)t;
+    below = (uint32_t)((t >> 63) & 1);
+#endif
+    return below;
+}
+
+// r = a + b over 8 limbs, returns the carry-out limb (0/1).
+HADES_DEV uint32_t add8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t carry;
+#if !HADES_EMUL
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(carry)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint64_t s = 0;
+    for (int k = 0; k < 8; k++) {
+        s = (uint64_t)a[k] + b[k] + (s >> 32);
+        r[k] = (uint32_t)s;
+    }
+    carry = (uint32_t)(s >> 32);
+#endif
+    return carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reductions to the canonical range
+// ------------------------------------------------------------------------------------------------
+// (x, x8) -> (x, x8) - (p << S) if that is non-negative.
+template <int S>
+HADES_DEV void cond_sub_p_shl(uint32_t (&x)[8], uint32_t& x8) {
+    uint32_t d[8], d8;
+    uint32_t below = sub_p_shl<S>(d, d8, x, x8);
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = below ? x[k] : d[k];
+    x8 = below ? x8 : d8;
+}
+
+// r (9 limbs, value < 2^(LOG2+1) * p... precisely value < 2p << LOG2) -> canonical [0,p).
+// LOG2 = 0: value < 2p; 1: < 4p; 2: < 8p.
+template <int LOG2>
+HADES_DEV void canon(Fr& out, const uint32_t (&r)[9]) {
+    uint32_t x[8], x8 = r[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = r[k];
+    if constexpr (LOG2 >= 2) cond_sub_p_shl<2>(x, x8);
+    if constexpr (LOG2 >= 1) cond_sub_p_shl<1>(x, x8);
+    cond_sub_p_shl<0>(x, x8);
+    HADES_ASSERT(x8 == 0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out.l[k] = x[k];
+}
+
+// out = a + b mod p, inputs canonical (scalar.rs:28 `*w += c`)
+HADES_DEV void fr_add(Fr& out, const Fr& a, const Fr& b) {
+    uint32_t s[8];
+    uint32_t c = add8(s, a.l, b.l);  // a + b < 2p < 2^256: c == 0
+    cond_sub_p_shl<0>(s, c);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out.l[k] = s[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// N-term Montgomery dot product:  r = (sum_j A_j * B_j) / 2^256  (mod p, NOT yet canonical).
+// `vec(j,k)` yields limb k of the operand walked by the inner chains, `sca(j,i)` limb i of the
+// operand consumed one limb per outer step.  Result: 9 limbs, value < p * (1 + sum_j A_j*B_j/(p*R)).
+// Even/odd bookkeeping per outer step i (all indices compile-time, so the "shift" is renaming):
+//   E holds limb positions 0..8 of the running sum, O positions 1..9, X one pending limb at 0.
+// ------------------------------------------------------------------------------------------------
+template <int N, bool kFirst, class Vec, class Sca>
+HADES_DEV void dot_step(uint32_t (&E)[9], uint32_t (&O)[9], uint32_t x, int i, Vec vec, Sca sca) {
+    // odd limbs of every term -> O (positions 1..8); the first chain also folds the pending limb in
+    if constexpr (kFirst) {
+        cmad4(O, vec(0, 1), vec(0, 3), vec(0, 5), vec(0, 7), sca(0, i));
+    } else {
+        cmad4_shiftin(O, vec(0, 1), vec(0, 3), vec(0, 5), vec(0, 7), sca(0, i), E[0], x);
+    }
+#pragma unroll
+    for (int j = 1; j < N; j++) cmad4(O, vec(j, 1), vec(j, 3), vec(j, 5), vec(j, 7), sca(j, i));
+    // even limbs -> E (positions 0..7)
+#pragma unroll
+    for (int j = 0; j < N; j++) cmad4(E, vec(j, 0), vec(j, 2), vec(j, 4), vec(j, 6), sca(j, i));
+    // Montgomery step: m = -E[0]; add m*p so that position 0 clears
+    uint32_t m = 0u - E[0];
+    cmad4(O, p_limb(1), p_limb(3), p_limb(5), p_limb(7), m);
+    redc_even(E, m);
+}
+
+template <int N, class Vec, class Sca>
+HADES_DEV void dot_mont(uint32_t (&r)[9], Vec vec, Sca sca) {
+    uint32_t A[9], B[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) A[k] = B[k] = 0;
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        // step i: E = A, O = B
+        if (i == 0) dot_step<N, true>(A, B, 0u, i, vec, sca);
+        else dot_step<N, false>(A, B, x, i, vec, sca);
+        // shift one limb: new E = B (positions 1..9 -> 0..8); new O[k] = A[k+2]; pending = A[1]
+        x = A[1];
+#pragma unroll
+        for (int k = 0; k < 7; k++) A[k] = A[k + 2];
+        A[7] = 0; A[8] = 0;
+        // step i+1: E = B, O = A
+        dot_step<N, false>(B, A, x, i + 1, vec, sca);
+        x = B[1];
+#pragma unroll
+        for (int k = 0; k < 7; k++) B[k] = B[k + 2];
+        B[7] = 0; B[8] = 0;
+    }
+    // after 8 steps: E = A (positions 0..8), O = B (positions 1..9), pending x at position 0
+    merge_even_odd(r, A, B, x);
+}
+
+// out = a*b/R mod p, canonical.  a,b canonical (or any a,b with a*b < p*R).
+HADES_DEV void fr_mul(Fr& out, const Fr& a, const Fr& b) {
+    uint32_t r[9];
+    dot_mont<1>(r, [&](int, int k) { return a.l[k]; }, [&](int, int i) { return b.l[i]; });
+    canon<0>(out, r);
+}
+
+// non-canonical product for internal chains: result < p*(1 + a*b/(p*R)) < 2^256 when a,b < 2p-ish
+HADES_DEV void fr_mul_lazy(Fr& out, const Fr& a, const Fr& b) {
+    uint32_t r[9];
+    dot_mont<1>(r, [&](int, int k) { return a.l[k]; }, [&](int, int i) { return b.l[i]; });
+    HADES_ASSERT(r[8] == 0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out.l[k] = r[k];
+}
+
+// x -> x^5 (scalar.rs:32-34 `value.square().square() * value`), canonical in, canonical out.
+// Bounds with x < p (p/R = 0.4528): x^2 < 1.453p, x^4 < 1.956p, x^5 < 1.886p -- all below 2^256,
+// so only the last product needs the conditional subtraction.
+HADES_DEV void fr_sbox(Fr& x) {
+    Fr x2, x4;
+    fr_mul_lazy(x2, x, x);
+    fr_mul_lazy(x4, x2, x2);
+    fr_mul(x, x4, x);
+}
+
+}  // namespace hades

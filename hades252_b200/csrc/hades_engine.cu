@@ -1,0 +1,558 @@
+// libhades_b200.so -- host side of the batched Hades252 engine: context, constant upload,
+// multi-device sharding, chunked H2D/compute/D2H pipeline, Merkle and sponge drivers, C ABI
+// (include/hades_cuda.h).  No CPU fallback anywhere: every entry point either runs CUDA kernels
+// or fails with a status code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hades_cuda.h"
+#include "kernels.cuh"
+
+using namespace hades;
+
+namespace {
+
+constexpr int kNumBuf = 3;                       // chunk buffers (and streams) per device
+constexpr size_t kChunkBytes = (size_t)96 << 20;  // target bytes per pipeline chunk
+
+struct DeviceState {
+    int ordinal = 0;
+    cudaStream_t streams[kNumBuf] = {nullptr, nullptr, nullptr};
+    uint64_t* chunk[kNumBuf] = {nullptr, nullptr, nullptr};
+    size_t chunk_bytes = 0;
+};
+
+thread_local std::string g_init_error;
+
+}  // namespace
+
+struct hades_ctx {
+    uint32_t width = 0;
+    std::vector<DeviceState> devs;
+    mutable std::string err;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+std::mutex g_tables_mutex;
+// (device ordinal, width or 0 for ark) -> bytes resident in __constant__ memory
+std::map<std::pair<int, int>, std::vector<uint64_t>> g_tables;
+
+int fail(hades_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_init_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                            \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, HADES_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                           \
+    } while (0)
+
+bool valid_dev(const hades_ctx* ctx, int dev_index) { return ctx && dev_index >= 0 && dev_index < (int)ctx->devs.size(); }
+
+int upload_table(hades_ctx* ctx, int ordinal, int key, const void* symbol, const uint64_t* limbs, size_t n_u64) {
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    auto it = g_tables.find({ordinal, key});
+    if (it != g_tables.end()) {
+        if (it->second.size() != n_u64 || memcmp(it->second.data(), limbs, n_u64 * 8) != 0)
+            return fail(ctx, HADES_ERR_CONSTANTS,
+                        "constant table (device %d, %s) already resident with different contents", ordinal,
+                        key ? "mds" : "ark");
+        return HADES_OK;
+    }
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(symbol, limbs, n_u64 * 8, 0, cudaMemcpyHostToDevice));
+    g_tables[{ordinal, key}] = std::vector<uint64_t>(limbs, limbs + n_u64);
+    return HADES_OK;
+}
+
+template <int W>
+int launch_perm(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t stream) {
+    if (n == 0) return HADES_OK;
+    size_t blocks = (n + kPermThreads - 1) / kPermThreads;
+    if (blocks > 0x7fffffffULL) return fail(ctx, HADES_ERR_INVALID_ARG, "batch too large for one launch");
+    perm_batch_kernel<W><<<(unsigned)blocks, kPermThreads, 0, stream>>>(reinterpret_cast<uint4*>(d_states), n);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HADES_OK;
+}
+
+int launch_perm_w(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t stream) {
+    switch (ctx->width) {
+        case 3: return launch_perm<3>(ctx, d_states, n, stream);
+        case 5: return launch_perm<5>(ctx, d_states, n, stream);
+        case 9: return launch_perm<9>(ctx, d_states, n, stream);
+    }
+    return fail(ctx, HADES_ERR_INVALID_ARG, "unsupported width %u", ctx->width);
+}
+
+int ensure_chunks(hades_ctx* ctx, DeviceState& d, size_t bytes) {
+    if (d.chunk_bytes >= bytes) return HADES_OK;
+    for (int b = 0; b < kNumBuf; b++) {
+        if (d.chunk[b]) CUDA_TRY(ctx, cudaFree(d.chunk[b]));
+        d.chunk[b] = nullptr;
+    }
+    d.chunk_bytes = 0;
+    for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaMalloc(&d.chunk[b], bytes));
+    d.chunk_bytes = bytes;
+    return HADES_OK;
+}
+
+int merkle_reduce(hades_ctx* ctx, const uint64_t* d_nodes, size_t n_nodes, int levels, uint64_t* d_scratch,
+                  uint64_t* d_out, cudaStream_t stream) {
+    const uint64_t* in = d_nodes;
+    uint64_t* bufA = d_scratch;
+    uint64_t* bufB = d_scratch + (n_nodes / 4) * 4;
+    size_t n = n_nodes;
+    for (int l = 0; l < levels; l++) {
+        size_t n_out = n / 4;
+        uint64_t* out = (l == levels - 1) ? d_out : ((l & 1) ? bufB : bufA);
+        size_t blocks = (n_out + kPermThreads - 1) / kPermThreads;
+        merkle_level_kernel<<<(unsigned)blocks, kPermThreads, 0, stream>>>(reinterpret_cast<const uint4*>(in),
+                                                                         reinterpret_cast<uint4*>(out), n_out);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        in = out;
+        n = n_out;
+    }
+    return HADES_OK;
+}
+
+int log4_exact(size_t n) {  // k if n == 4^k else -1
+    if (n == 0 || (n & (n - 1))) return -1;
+    int lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    return (lg & 1) ? -1 : lg / 2;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, const uint64_t* ark_limbs,
+               size_t n_ark, const uint64_t* mds_limbs) {
+    if (!out || !ark_limbs || !mds_limbs || n_dev < 1)
+        return fail(nullptr, HADES_ERR_INVALID_ARG, "hades_init: null pointer or n_dev < 1");
+    *out = nullptr;
+    if (width != 3 && width != 5 && width != 9)
+        return fail(nullptr, HADES_ERR_INVALID_ARG, "hades_init: width %u not built (kernels exist for 3, 5, 9)", width);
+    if ((size_t)kRounds * width > n_ark)
+        return fail(nullptr, HADES_ERR_OUT_OF_CONSTANTS, "Hades252 out of ARK constants: need %zu, got %zu",
+                    (size_t)kRounds * width, n_ark);
+    if (n_ark > HADES_N_ROUND_CONSTANTS) n_ark = HADES_N_ROUND_CONSTANTS;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1)
+        return fail(nullptr, HADES_ERR_NO_DEVICE, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    hades_ctx* ctx = new hades_ctx();
+    ctx->width = width;
+    int rc = HADES_OK;
+    for (int g = 0; g < n_dev && rc == HADES_OK; g++) {
+        DeviceState d;
+        d.ordinal = devices ? devices[g] : g;
+        if (d.ordinal < 0 || d.ordinal >= count) {
+            rc = fail(nullptr, HADES_ERR_NO_DEVICE, "device ordinal %d out of range (0..%d)", d.ordinal, count - 1);
+            break;
+        }
+        ctx->devs.push_back(d);
+    }
+    for (size_t g = 0; g < ctx->devs.size() && rc == HADES_OK; g++) {
+        DeviceState& d = ctx->devs[g];
+        auto step = [&]() -> int {
+            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+            for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d.streams[b], cudaStreamNonBlocking));
+            int r = upload_table(ctx, d.ordinal, 0, c_ark, ark_limbs, n_ark * 4);
+            if (r) return r;
+            const void* sym = width == 3 ? (const void*)c_mds3 : width == 5 ? (const void*)c_mds5 : (const void*)c_mds9;
+            return upload_table(ctx, d.ordinal, (int)width, sym, mds_limbs, (size_t)width * width * 4);
+        };
+        rc = step();
+    }
+    if (rc != HADES_OK) {
+        g_init_error = ctx->err.empty() ? g_init_error : ctx->err;
+        hades_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return HADES_OK;
+}
+
+void hades_destroy(hades_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.ordinal);
+        for (int b = 0; b < kNumBuf; b++) {
+            if (d.streams[b]) cudaStreamSynchronize(d.streams[b]);
+            if (d.chunk[b]) cudaFree(d.chunk[b]);
+            if (d.streams[b]) cudaStreamDestroy(d.streams[b]);
+        }
+    }
+    delete ctx;
+}
+
+const char* hades_last_error(const hades_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+uint32_t hades_width(const hades_ctx* ctx) { return ctx ? ctx->width : 0; }
+int hades_device_count(const hades_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+uint64_t hades_launch_count(const hades_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hades_perm_batch_dev(hades_ctx* ctx, int dev_index, uint64_t* d_states, size_t n, void* stream) {
+    if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    if (n == 0) return HADES_OK;
+    if (!d_states || ((uintptr_t)d_states & 15)) return fail(ctx, HADES_ERR_INVALID_ARG, "d_states must be non-null and 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    return launch_perm_w(ctx, d_states, n, (cudaStream_t)stream);
+}
+
+int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
+    if (!ctx) return fail(ctx, HADES_ERR_INVALID_ARG, "null context");
+    if (n == 0) return HADES_OK;
+    if (!host_states) return fail(ctx, HADES_ERR_INVALID_ARG, "null states pointer");
+    const size_t state_bytes = (size_t)ctx->width * 32;
+    const size_t G = ctx->devs.size();
+    size_t chunk_states = std::max<size_t>(kPermThreads, kChunkBytes / state_bytes / kPermThreads * kPermThreads);
+    // small batches: split so that all three stages still overlap
+    size_t per_dev = (n + G - 1) / G;
+    if (per_dev < chunk_states * kNumBuf)
+        chunk_states = std::max<size_t>(kPermThreads, (per_dev / kNumBuf + kPermThreads) / kPermThreads * kPermThreads);
+    std::vector<size_t> lo(G), hi(G), next(G);
+    size_t max_chunks = 0;
+    for (size_t g = 0; g < G; g++) {
+        lo[g] = n * g / G;
+        hi[g] = n * (g + 1) / G;
+        next[g] = lo[g];
+        if (hi[g] > lo[g]) {
+            CUDA_TRY(ctx, cudaSetDevice(ctx->devs[g].ordinal));
+            int r = ensure_chunks(ctx, ctx->devs[g], std::min(chunk_states, hi[g] - lo[g]) * state_bytes);
+            if (r) return r;
+            max_chunks = std::max(max_chunks, (hi[g] - lo[g] + chunk_states - 1) / chunk_states);
+        }
+    }
+    int rc = HADES_OK;
+    for (size_t c = 0; c < max_chunks && rc == HADES_OK; c++) {
+        for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+            if (next[g] >= hi[g]) continue;
+            DeviceState& d = ctx->devs[g];
+            size_t cnt = std::min(chunk_states, hi[g] - next[g]);
+            int b = (int)(c % kNumBuf);
+            uint64_t* h = host_states + next[g] * ctx->width * 4;
+            auto step = [&]() -> int {
+                CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d.chunk[b], h, cnt * state_bytes, cudaMemcpyHostToDevice, d.streams[b]));
+                int r = launch_perm_w(ctx, d.chunk[b], cnt, d.streams[b]);
+                if (r) return r;
+                CUDA_TRY(ctx, cudaMemcpyAsync(h, d.chunk[b], cnt * state_bytes, cudaMemcpyDeviceToHost, d.streams[b]));
+                return HADES_OK;
+            };
+            rc = step();
+            next[g] += cnt;
+        }
+    }
+    for (size_t g = 0; g < G; g++) {
+        cudaSetDevice(ctx->devs[g].ordinal);
+        for (int b = 0; b < kNumBuf; b++) {
+            cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[b]);
+            if (e != cudaSuccess && rc == HADES_OK)
+                rc = fail(ctx, HADES_ERR_CUDA, "perm_batch pipeline failed on device %d: %s", ctx->devs[g].ordinal,
+                          cudaGetErrorString(e));
+        }
+    }
+    return rc;
+}
+
+int hades_merkle_reduce_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_nodes, size_t n_nodes, int levels,
+                            uint64_t* d_scratch, uint64_t* d_out, void* stream) {
+    if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+    if (levels < 0 || !d_nodes || !d_out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer or negative levels");
+    if (levels > 31 || (n_nodes >> (2 * levels)) == 0 || (n_nodes & (((size_t)1 << (2 * levels)) - 1)))
+        return fail(ctx, HADES_ERR_NOT_POWER_OF_4, "n_nodes=%zu is not a multiple of 4^%d", n_nodes, levels);
+    if (levels > 1 && !d_scratch) return fail(ctx, HADES_ERR_INVALID_ARG, "scratch required for more than one level");
+    if (((uintptr_t)d_nodes | (uintptr_t)d_out | (uintptr_t)d_scratch) & 15)
+        return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    if (levels == 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_out, d_nodes, n_nodes * 32, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return HADES_OK;
+    }
+    return merkle_reduce(ctx, d_nodes, n_nodes, levels, d_scratch, d_out, (cudaStream_t)stream);
+}
+
+int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]) {
+    if (!ctx || !host_leaves || !root) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+    int depth = log4_exact(n_leaves);
+    if (depth < 0) return fail(ctx, HADES_ERR_NOT_POWER_OF_4, "number of leaves (%zu) must be a power of 4", n_leaves);
+    if (depth == 0) {
+        memcpy(root, host_leaves, 32);
+        return HADES_OK;
+    }
+    // use the largest power-of-two device count that leaves >= 4 whole subtrees' worth of work each
+    size_t G = 1;
+    while (G * 2 <= ctx->devs.size() && n_leaves / (G * 2) >= 1024) G *= 2;
+    size_t per_dev = n_leaves / G;                 // = 4^a or 2*4^a
+    int sub_levels = 0;                            // levels each device can reduce on its own range
+    while (((per_dev >> (2 * (sub_levels + 1))) << (2 * (sub_levels + 1))) == per_dev && (per_dev >> (2 * (sub_levels + 1))) >= 1)
+        sub_levels++;
+    size_t roots_per_dev = per_dev >> (2 * sub_levels);  // 1 or 2
+    size_t n_roots = roots_per_dev * G;
+    std::vector<uint64_t> roots(n_roots * 4);
+    struct Bufs { uint64_t *leaves = nullptr, *scratch = nullptr, *out = nullptr; };
+    std::vector<Bufs> bufs(G);
+    int rc = HADES_OK;
+    auto cleanup = [&]() {
+        for (size_t g = 0; g < G; g++) {
+            cudaSetDevice(ctx->devs[g].ordinal);
+            cudaFree(bufs[g].leaves); cudaFree(bufs[g].scratch); cudaFree(bufs[g].out);
+        }
+    };
+    for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+        auto step = [&]() -> int {
+            DeviceState& d = ctx->devs[g];
+            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].leaves, per_dev * 32));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].scratch, (per_dev / 4 + per_dev / 16 + 4) * 32));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].out, std::max<size_t>(roots_per_dev, 1) * 32));
+            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].leaves, host_leaves + g * per_dev * 4, per_dev * 32,
+                                          cudaMemcpyHostToDevice, d.streams[0]));
+            int r = merkle_reduce(ctx, bufs[g].leaves, per_dev, sub_levels, bufs[g].scratch, bufs[g].out, d.streams[0]);
+            if (r) return r;
+            CUDA_TRY(ctx, cudaMemcpyAsync(roots.data() + g * roots_per_dev * 4, bufs[g].out, roots_per_dev * 32,
+                                          cudaMemcpyDeviceToHost, d.streams[0]));
+            return HADES_OK;
+        };
+        rc = step();
+    }
+    for (size_t g = 0; g < G; g++) {
+        cudaSetDevice(ctx->devs[g].ordinal);
+        cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[0]);
+        if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "merkle subtree pass failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == HADES_OK && n_roots > 1) {
+        // top of the tree on the first device (n_roots <= 2*G nodes)
+        auto step = [&]() -> int {
+            DeviceState& d = ctx->devs[0];
+            int top_levels = log4_exact(n_roots);
+            if (top_levels < 0) return fail(ctx, HADES_ERR_NOT_POWER_OF_4, "internal: %zu subtree roots", n_roots);
+            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[0].leaves, roots.data(), n_roots * 32, cudaMemcpyHostToDevice, d.streams[0]));
+            int r = merkle_reduce(ctx, bufs[0].leaves, n_roots, top_levels, bufs[0].scratch, bufs[0].out, d.streams[0]);
+            if (r) return r;
+            CUDA_TRY(ctx, cudaMemcpyAsync(roots.data(), bufs[0].out, 32, cudaMemcpyDeviceToHost, d.streams[0]));
+            CUDA_TRY(ctx, cudaStreamSynchronize(d.streams[0]));
+            return HADES_OK;
+        };
+        rc = step();
+    }
+    cleanup();
+    if (rc == HADES_OK) memcpy(root, roots.data(), 32);
+    return rc;
+}
+
+int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
+                           size_t n_msgs, uint64_t* d_out, void* stream) {
+    if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "sponge needs a width-5 context");
+    if (n_msgs == 0) return HADES_OK;
+    if (!d_offsets || !d_out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    if (((uintptr_t)d_elems | (uintptr_t)d_out) & 15) return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    size_t blocks = (n_msgs + kPermThreads - 1) / kPermThreads;
+    sponge_kernel<<<(unsigned)blocks, kPermThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(d_elems), d_offsets, nullptr, reinterpret_cast<uint4*>(d_out), n_msgs);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HADES_OK;
+}
+
+int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs, uint64_t* out) {
+    if (!ctx) return fail(ctx, HADES_ERR_INVALID_ARG, "null context");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "sponge needs a width-5 context");
+    if (n_msgs == 0) return HADES_OK;
+    if (!offsets || !out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    const size_t n_elems = offsets[n_msgs] - offsets[0];
+    if (n_elems && !elems) return fail(ctx, HADES_ERR_INVALID_ARG, "null elems pointer");
+    for (size_t m = 0; m < n_msgs; m++)
+        if (offsets[m + 1] < offsets[m]) return fail(ctx, HADES_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    if (n_msgs > 0xffffffffULL) return fail(ctx, HADES_ERR_INVALID_ARG, "too many messages for one call");
+    // order messages by block count so that the 32 messages of a warp need the same number of perms
+    std::vector<uint32_t> order(n_msgs);
+    {
+        size_t max_blocks = 0;
+        for (size_t m = 0; m < n_msgs; m++) max_blocks = std::max<size_t>(max_blocks, (offsets[m + 1] - offsets[m]) / 4 + 1);
+        std::vector<size_t> start(max_blocks + 2, 0);
+        for (size_t m = 0; m < n_msgs; m++) start[(offsets[m + 1] - offsets[m]) / 4 + 2]++;
+        for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+        for (size_t m = 0; m < n_msgs; m++) order[start[(offsets[m + 1] - offsets[m]) / 4 + 1]++] = (uint32_t)m;
+    }
+    // shard the ORDERED message list over the devices (interleaved so every device sees every length)
+    const size_t G = std::min<size_t>(ctx->devs.size(), std::max<size_t>(1, n_msgs / 4096));
+    struct Bufs { uint64_t *elems = nullptr, *offsets = nullptr, *out = nullptr; uint32_t* order = nullptr; };
+    std::vector<Bufs> bufs(G);
+    std::vector<std::vector<uint32_t>> dev_order(G);
+    for (size_t t = 0; t < n_msgs; t++) dev_order[(t / 32) % G].push_back(order[t]);
+    int rc = HADES_OK;
+    for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+        auto step = [&]() -> int {
+            DeviceState& d = ctx->devs[g];
+            size_t cnt = dev_order[g].size();
+            if (!cnt) return HADES_OK;
+            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+            // every device receives the whole CSR arrays (elements are read-only and shared);
+            // only `order` and the written digests are per device
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].elems, std::max<size_t>(n_elems, 1) * 32));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].offsets, (n_msgs + 1) * 8));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].out, n_msgs * 32));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].order, cnt * 4));
+            if (n_elems)
+                CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].elems, elems + offsets[0] * 4, n_elems * 32, cudaMemcpyHostToDevice, d.streams[0]));
+            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].offsets, offsets, (n_msgs + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
+            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].order, dev_order[g].data(), cnt * 4, cudaMemcpyHostToDevice, d.streams[0]));
+            size_t blocks = (cnt + kPermThreads - 1) / kPermThreads;
+            // offsets are absolute: bias the element base pointer by offsets[0]
+            const uint4* ebase = reinterpret_cast<const uint4*>(bufs[g].elems) - offsets[0] * 2;
+            sponge_kernel<<<(unsigned)blocks, kPermThreads, 0, d.streams[0]>>>(ebase, bufs[g].offsets, bufs[g].order,
+                                                                             reinterpret_cast<uint4*>(bufs[g].out), cnt);
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaGetLastError());
+            if (G == 1) CUDA_TRY(ctx, cudaMemcpyAsync(out, bufs[g].out, n_msgs * 32, cudaMemcpyDeviceToHost, d.streams[0]));
+            return HADES_OK;
+        };
+        rc = step();
+    }
+    std::vector<uint64_t> tmp;
+    for (size_t g = 0; g < G; g++) {
+        cudaSetDevice(ctx->devs[g].ordinal);
+        cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[0]);
+        if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "sponge pass failed: %s", cudaGetErrorString(e));
+        if (rc == HADES_OK && G > 1 && !dev_order[g].empty()) {
+            // digests were scattered by message index into a full-size buffer: pick this device's
+            tmp.resize(n_msgs * 4);
+            e = cudaMemcpy(tmp.data(), bufs[g].out, n_msgs * 32, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = fail(ctx, HADES_ERR_CUDA, "sponge D2H failed: %s", cudaGetErrorString(e));
+            else for (uint32_t m : dev_order[g]) memcpy(out + (size_t)m * 4, tmp.data() + (size_t)m * 4, 32);
+        }
+        cudaFree(bufs[g].elems); cudaFree(bufs[g].offsets); cudaFree(bufs[g].out); cudaFree(bufs[g].order);
+    }
+    return rc;
+}
+
+int hades_host_register(hades_ctx* ctx, void* ptr, size_t bytes) {
+    if (!ctx || !ptr) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
+    CUDA_TRY(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return HADES_OK;
+}
+int hades_host_unregister(hades_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    CUDA_TRY(ctx, cudaHostUnregister(ptr));
+    return HADES_OK;
+}
+
+int hades_gen_elems_dev(hades_ctx* ctx, int dev_index, uint64_t* d_out, uint64_t first_elem, size_t n_elems,
+                        uint64_t seed, void* stream) {
+    if (!valid_dev(ctx, dev_index) || (!d_out && n_elems)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad argument");
+    if (!n_elems) return HADES_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    size_t blocks = std::min<size_t>((n_elems * 4 + 255) / 256, 148 * 16);
+    gen_elems_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_out, first_elem, n_elems, seed);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HADES_OK;
+}
+
+int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uint64_t first_limb, size_t n_limbs,
+                     uint64_t* d_digest, void* stream) {
+    if (!valid_dev(ctx, dev_index) || !d_digest || (!d_limbs && n_limbs)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad argument");
+    if (!n_limbs) return HADES_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    size_t blocks = std::min<size_t>((n_limbs + 255) / 256, 148 * 16);
+    digest_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_limbs, first_limb, n_limbs,
+                                                                    reinterpret_cast<unsigned long long*>(d_digest));
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HADES_OK;
+}
+
+int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products_per_s) {
+    if (!valid_dev(ctx, dev_index) || !products_per_s || variant < 0 || variant > 3)
+        return fail(ctx, HADES_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    const int threads = 256, blocks = 148 * 8;
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    std::vector<uint32_t> h(128);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (uint32_t)splitmix64(i + 1) | 1u;
+    CUDA_TRY(ctx, cudaMalloc(&d_in, h.size() * 4));
+    CUDA_TRY(ctx, cudaMalloc(&d_out, (size_t)threads * blocks * 4));
+    CUDA_TRY(ctx, cudaMemcpy(d_in, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    auto launch = [&](int iters) {
+        switch (variant) {
+            case 0: imad_peak_kernel<0><<<blocks, threads>>>(d_in, d_out, iters); break;
+            case 1: imad_peak_kernel<1><<<blocks, threads>>>(d_in, d_out, iters); break;
+            case 2: imad_peak_kernel<2><<<blocks, threads>>>(d_in, d_out, iters); break;
+            default: imad_peak_kernel<3><<<blocks, threads>>>(d_in, d_out, iters); break;
+        }
+        ctx->launches++;
+    };
+    launch(64);  // warm-up
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    const int iters = 4096;
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CUDA_TRY(ctx, cudaEventRecord(e0));
+        launch(iters);
+        CUDA_TRY(ctx, cudaEventRecord(e1));
+        CUDA_TRY(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        // per thread and iteration: 8 unrolled steps x 8 products
+        double prods = (double)threads * blocks * (double)iters * 8.0 * 8.0;
+        best = std::max(best, prods / (ms * 1e-3));
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_in); cudaFree(d_out);
+    *products_per_s = best;
+    return HADES_OK;
+}
+
+int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
+                      int* max_threads_per_block) {
+    if (!ctx || !kernel) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    const void* fn = nullptr;
+    if (!strcmp(kernel, "perm3")) fn = (const void*)perm_batch_kernel<3>;
+    else if (!strcmp(kernel, "perm5")) fn = (const void*)perm_batch_kernel<5>;
+    else if (!strcmp(kernel, "perm9")) fn = (const void*)perm_batch_kernel<9>;
+    else if (!strcmp(kernel, "merkle")) fn = (const void*)merkle_level_kernel;
+    else if (!strcmp(kernel, "sponge")) fn = (const void*)sponge_kernel;
+    else return fail(ctx, HADES_ERR_INVALID_ARG, "unknown kernel '%s'", kernel);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
+    cudaFuncAttributes a;
+    CUDA_TRY(ctx, cudaFuncGetAttributes(&a, fn));
+    if (regs_per_thread) *regs_per_thread = a.numRegs;
+    if (local_bytes) *local_bytes = (int)a.localSizeBytes;
+    if (max_threads_per_block) *max_threads_per_block = a.maxThreadsPerBlock;
+    return HADES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""Host-side mirror of the reference crate's public surface for the `perm` path.
+
+Reference (paths relative to /root/reference):
+  * consts `TOTAL_FULL_ROUNDS`, `PARTIAL_ROUNDS`, `WIDTH`          src/lib.rs:20-27
+  * `trait Strategy` with `perm(&mut self, data: &mut [T])`, `rounds()`   src/strategies.rs:31,140-162
+  * `ScalarStrategy::new()`                                          src/strategies/scalar.rs:12-20
+`CudaStrategy` is the added device strategy (BASELINE.json north_star): same `perm` contract
+(in-place, length must equal WIDTH) plus the batched `perm_batch(&mut [[BlsScalar; WIDTH]])`.
+Everything runs through the C ABI of libhades_b200.so (include/hades_cuda.h); this module holds
+no arithmetic and no CPU fallback.
+
+States are numpy uint64 arrays of Montgomery limbs, shape [n, WIDTH, 4]: exactly the bytes of the
+reference's `[[BlsScalar; WIDTH]]`.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native, constants
+
+TOTAL_FULL_ROUNDS = 8   # lib.rs:22
+PARTIAL_ROUNDS = 59     # lib.rs:26
+WIDTH = 5               # lib.rs:27
+
+
+class HadesError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"hades status {status}: {message}")
+        self.status = status
+
+
+class Strategy:
+    """strategies.rs:31 -- the algorithm interface; implementors provide `perm`."""
+
+    def perm(self, data) -> None:  # strategies.rs:140
+        raise NotImplementedError
+
+    @staticmethod
+    def rounds() -> int:  # strategies.rs:160-162
+        return TOTAL_FULL_ROUNDS + PARTIAL_ROUNDS
+
+
+def _as_u64(a: np.ndarray, what: str) -> np.ndarray:
+    if not isinstance(a, np.ndarray) or a.dtype != np.uint64 or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"{what} must be a C-contiguous numpy uint64 array (Montgomery limbs)")
+    return a
+
+
+class CudaStrategy(Strategy):
+    """Batched device strategy.  `devices`: CUDA ordinals to shard over (default: device 0)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, width: int = WIDTH):
+        self._lib = _native.lib()
+        self._ctx = _native.ctx_p()
+        self.width = int(width)
+        devs = list(devices) if devices is not None else [0]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        ark = np.ascontiguousarray(constants.round_constants())
+        mds = np.ascontiguousarray(constants.mds_matrix(self.width)) if self.width in (3, 5, 9) else np.zeros((1, 4), np.uint64)
+        rc = self._lib.hades_init(ctypes.byref(self._ctx), arr, len(devs), self.width,
+                                  ark.ctypes.data_as(_native.u64p), ark.shape[0], mds.ctypes.data_as(_native.u64p))
+        if rc:
+            msg = self._lib.hades_last_error(None).decode()
+            self._ctx = None
+            raise HadesError(rc, msg)
+        self.devices = devs
+
+    @classmethod
+    def new(cls, devices: Optional[Sequence[int]] = None) -> "CudaStrategy":  # scalar.rs:17-19 analogue
+        return cls(devices)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.hades_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise HadesError(rc, self._lib.hades_last_error(self._ctx).decode())
+
+    # ------------------------------------------------------------------ the reference path
+    def perm(self, data: np.ndarray) -> None:
+        """`Strategy::perm` on ONE state, in place.  Like the reference's `mul_matrix`
+        (scalar.rs:48 `copy_from_slice`), a length other than WIDTH is a programmer error."""
+        _as_u64(data, "data")
+        if data.shape != (self.width, 4):
+            raise ValueError(f"perm needs exactly WIDTH={self.width} scalars of 4 limbs, got shape {data.shape}")
+        self._check(self._lib.hades_perm_batch(self._ctx, data.ctypes.data, 1))
+
+    def perm_batch(self, states: np.ndarray) -> None:
+        """`perm_batch(&mut [[BlsScalar; WIDTH]])`: n states, in place, host memory."""
+        _as_u64(states, "states")
+        if states.ndim != 3 or states.shape[1:] != (self.width, 4):
+            raise ValueError(f"states must have shape [n, {self.width}, 4], got {states.shape}")
+        self._check(self._lib.hades_perm_batch(self._ctx, states.ctypes.data, states.shape[0]))
+
+    def perm_batch_ptr(self, host_ptr: int, n: int) -> None:
+        """Same on a raw host address (e.g. a pinned torch tensor's data_ptr())."""
+        self._check(self._lib.hades_perm_batch(self._ctx, host_ptr, n))
+
+    def perm_batch_device(self, device_ptr: int, n: int, stream: int = 0, dev_index: int = 0) -> None:
+        """Device-resident, asynchronous on `stream` (a cudaStream_t value)."""
+        self._check(self._lib.hades_perm_batch_dev(self._ctx, dev_index, device_ptr, n, stream))
+
+    # ------------------------------------------------------------------ compositions of perm
+    def merkle_root(self, leaves: np.ndarray) -> np.ndarray:
+        """4-ary Merkle root; leaves uint64 [4^k, 4]."""
+        _as_u64(leaves, "leaves")
+        if leaves.ndim != 2 or leaves.shape[1] != 4:
+            raise ValueError("leaves must have shape [n, 4]")
+        root = np.empty(4, dtype=np.uint64)
+        self._check(self._lib.hades_merkle_root(self._ctx, leaves.ctypes.data, leaves.shape[0],
+                                                root.ctypes.data_as(_native.u64p)))
+        return root
+
+    def merkle_reduce_device(self, nodes_ptr: int, n_nodes: int, levels: int, scratch_ptr: int, out_ptr: int,
+                             stream: int = 0, dev_index: int = 0) -> None:
+        self._check(self._lib.hades_merkle_reduce_dev(self._ctx, dev_index, nodes_ptr, n_nodes, levels, scratch_ptr,
+                                                      out_ptr, stream))
+
+    def sponge_batch(self, elems: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """Sponge digests of n messages in CSR form; elems uint64 [total, 4], offsets uint64 [n+1]."""
+        _as_u64(offsets, "offsets")
+        if offsets.ndim != 1 or offsets.shape[0] < 1:
+            raise ValueError("offsets must be a 1-d array of n+1 entries")
+        n = offsets.shape[0] - 1
+        if elems.size:
+            _as_u64(elems, "elems")
+        out = np.empty((n, 4), dtype=np.uint64)
+        self._check(self._lib.hades_sponge_batch(self._ctx, elems.ctypes.data if elems.size else None,
+                                                 offsets.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def sponge_batch_device(self, elems_ptr: int, offsets_ptr: int, n_msgs: int, out_ptr: int, stream: int = 0,
+                            dev_index: int = 0) -> None:
+        self._check(self._lib.hades_sponge_batch_dev(self._ctx, dev_index, elems_ptr, offsets_ptr, n_msgs, out_ptr, stream))
+
+    # ------------------------------------------------------------------ measurement helpers
+    def gen_elems_device(self, out_ptr: int, first_elem: int, n_elems: int, seed: int, stream: int = 0,
+                         dev_index: int = 0) -> None:
+        self._check(self._lib.hades_gen_elems_dev(self._ctx, dev_index, out_ptr, first_elem, n_elems,
+                                                  seed & 0xFFFFFFFFFFFFFFFF, stream))
+
+    def digest_device(self, limbs_ptr: int, first_limb: int, n_limbs: int, digest_ptr: int, stream: int = 0,
+                      dev_index: int = 0) -> None:
+        self._check(self._lib.hades_digest_dev(self._ctx, dev_index, limbs_ptr, first_limb, n_limbs, digest_ptr, stream))
+
+    def imad_peak(self, variant: int, dev_index: int = 0) -> float:
+        v = ctypes.c_double()
+        self._check(self._lib.hades_imad_peak(self._ctx, dev_index, variant, ctypes.byref(v)))
+        return v.value
+
+    def kernel_info(self, kernel: str) -> dict:
+        regs, local, thr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.hades_kernel_info(self._ctx, kernel.encode(), ctypes.byref(regs), ctypes.byref(local),
+                                                ctypes.byref(thr)))
+        return {"regs_per_thread": regs.value, "local_bytes": local.value, "max_threads_per_block": thr.value}
+
+    def host_register(self, ptr: int, nbytes: int) -> None:
+        self._check(self._lib.hades_host_register(self._ctx, ptr, nbytes))
+
+    def host_unregister(self, ptr: int) -> None:
+        self._check(self._lib.hades_host_unregister(self._ctx, ptr))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.hades_launch_count(self._ctx))

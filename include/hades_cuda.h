@@ -1,0 +1,145 @@
+/*
+ * hades_cuda.h -- C ABI of the B200-native batched Hades252 engine (libhades_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of the reference crate dusk-hades 0.24.1:
+ * `ScalarStrategy::perm` (reference: src/strategies.rs:140-157 + src/strategies/scalar.rs:23-49),
+ * batched.  A Rust `CudaStrategy` (see INTEGRATION.md and bindings/rust/) binds exactly these
+ * symbols; nothing here depends on torch, Python or C++ types.
+ *
+ * Data format (identical to the reference's in-memory `BlsScalar`, so no conversion either side):
+ *   field element = 4 little-endian uint64_t limbs of the MONTGOMERY form x*2^256 mod p, fully
+ *   reduced (< p);  a width-W state = W consecutive elements (W*32 bytes);  a batch = n consecutive
+ *   states (array-of-structs), i.e. the memory of `&mut [[BlsScalar; WIDTH]]`.
+ *   Inputs >= p are a caller contract violation (a `BlsScalar` can never hold them).
+ *
+ * All functions return 0 on success or a non-zero hades_status; hades_last_error() gives the
+ * message.  There is no CPU fallback: without a usable CUDA device hades_init fails.
+ *
+ * Threading: one hades_ctx is single-caller (mirrors `&mut self`); distinct contexts may be used
+ * concurrently.  The constant tables live in per-device `__constant__` memory and are therefore
+ * shared by all contexts of a process on that device (in the reference they are compile-time
+ * constants of the crate): re-initialising a (device,width) with DIFFERENT tables is an error.
+ */
+#ifndef HADES_CUDA_H
+#define HADES_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference: src/lib.rs:20-27 */
+#define HADES_TOTAL_FULL_ROUNDS 8
+#define HADES_PARTIAL_ROUNDS 59
+#define HADES_WIDTH 5
+#define HADES_N_ROUND_CONSTANTS 960 /* src/round_constants.rs:16 */
+
+typedef enum hades_status {
+    HADES_OK = 0,
+    HADES_ERR_INVALID_ARG = 1,   /* null pointer, bad width, misaligned device pointer, ... */
+    HADES_ERR_NOT_POWER_OF_4 = 2,/* merkle: number of leaves is not 4^k, k >= 0 */
+    HADES_ERR_CUDA = 3,          /* a CUDA runtime call failed; see hades_last_error */
+    HADES_ERR_NO_DEVICE = 4,     /* no CUDA device / requested ordinal does not exist */
+    HADES_ERR_CONSTANTS = 5,     /* tables differ from the ones already resident for this width */
+    HADES_ERR_OUT_OF_CONSTANTS = 6 /* 67*width > n_ark: "Hades252 out of ARK constants", strategies.rs:40 */
+} hades_status;
+
+typedef struct hades_ctx hades_ctx;
+
+/*
+ * Create a context over `n_dev` CUDA devices (ordinals in `devices`; NULL => device 0 only when
+ * n_dev == 1, or devices 0..n_dev-1) and upload the constant tables once.
+ *   width      permutation width; kernels exist for 3, 5 (the reference's WIDTH, lib.rs:27) and 9.
+ *   ark_limbs  n_ark*4 u64: the raw limbs of `ROUND_CONSTANTS` (src/round_constants.rs:29-48), i.e.
+ *              AFTER `BlsScalar::from_raw`.  Round r uses entries [r*width, r*width+width).
+ *   mds_limbs  width*width*4 u64: raw limbs of `MDS_MATRIX` row-major (src/mds_matrix.rs:18-40).
+ * Replaces: the compile-time const tables of the crate (they become `__constant__` memory).
+ */
+int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width,
+               const uint64_t* ark_limbs, size_t n_ark, const uint64_t* mds_limbs);
+void hades_destroy(hades_ctx* ctx);
+
+/* Message of the last failure on this context (or of the last failed hades_init when ctx == NULL).
+ * Valid until the next call on the same context / thread. */
+const char* hades_last_error(const hades_ctx* ctx);
+
+uint32_t hades_width(const hades_ctx* ctx);
+int hades_device_count(const hades_ctx* ctx);
+
+/*
+ * `CudaStrategy::perm_batch(&mut [[BlsScalar; WIDTH]])`: permute n states in place.
+ * HOST pointer.  Sharded in contiguous ranges over the context's devices, each range streamed in
+ * chunks (H2D / kernel / D2H overlapped on separate streams).  Synchronous: on return the host
+ * buffer holds the outputs.  Pinned (page-locked) host memory makes the copies asynchronous; see
+ * hades_host_register.  Replaces: a loop of `ScalarStrategy::perm` (strategies.rs:140).
+ */
+int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n);
+
+/*
+ * Device-resident variant: d_states is device memory on devices[dev_index], 16-byte aligned.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = the legacy default stream); no host sync.
+ */
+int hades_perm_batch_dev(hades_ctx* ctx, int dev_index, uint64_t* d_states, size_t n, void* stream);
+
+/*
+ * 4-ary Merkle root: node = perm([15, c0, c1, c2, c3])[1] (bitmask of present children in word 0,
+ * output word 1); leaves are field elements used as level-0 nodes; n_leaves = 4^k.  Width-5 contexts
+ * only.  HOST pointers; leaf ranges are sharded over the context's devices, subtree roots are
+ * gathered and the top levels finished on the first device.  (Build-defined composition: the
+ * reference removed its Merkle code in 0.7.0, CHANGELOG.md:159-162.)
+ */
+int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]);
+
+/*
+ * Device-resident Merkle reduction: hashes `levels` levels, n_nodes -> n_nodes / 4^levels nodes.
+ * d_nodes is read only; d_scratch must hold n_nodes/4 + n_nodes/16 elements (32 B each); the
+ * result is written to d_out (n_nodes / 4^levels elements).  Asynchronous on `stream`.
+ * This is the per-GPU step of the sharded tree: each rank reduces its leaf range to subtree roots,
+ * roots are all-gathered (NCCL), and the top levels are reduced with the same call.
+ */
+int hades_merkle_reduce_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_nodes, size_t n_nodes,
+                            int levels, uint64_t* d_scratch, uint64_t* d_out, void* stream);
+
+/*
+ * Sponge hash (rate 4, capacity 1) of n_msgs variable-length messages given in CSR form:
+ * message m = elems[offsets[m] .. offsets[m+1]) (field elements, 32 B each).  State [0;5]; the
+ * message is padded with a single 1 then zeros to a multiple of 4 (always at least the 1); each
+ * block is added into words 1..4 and permuted; digest = word 1.  out: n_msgs*4 u64.  HOST pointers.
+ */
+int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs,
+                       uint64_t* out);
+/* Device-resident variant (all pointers on devices[dev_index]); asynchronous on `stream`. */
+int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
+                           size_t n_msgs, uint64_t* d_out, void* stream);
+
+/* Page-lock / unlock a caller-owned host range so hades_perm_batch copies run asynchronously. */
+int hades_host_register(hades_ctx* ctx, void* ptr, size_t bytes);
+int hades_host_unregister(hades_ctx* ctx, void* ptr);
+
+/* ---- measurement helpers (bench / tests); not part of the reference-facing surface ---------- */
+
+/* Fill d_out with n_elems synthetic field elements: element e (global index first_elem + i), limb l
+ * = splitmix64(seed + 4*e + l), top limb masked to 62 bits (< 2^254 < p).  SURVEY.md 8(d). */
+int hades_gen_elems_dev(hades_ctx* ctx, int dev_index, uint64_t* d_out, uint64_t first_elem, size_t n_elems,
+                        uint64_t seed, void* stream);
+/* Accumulate a 4-word digest of n_limbs u64 into d_digest[4] (device memory, caller-zeroed):
+ * [0] ^= H, [1] += H, [2] ^= limb, [3] += limb, H = splitmix64(limb ^ splitmix64(first_limb + i)). */
+int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uint64_t first_limb, size_t n_limbs,
+                     uint64_t* d_digest, void* stream);
+/* Integer-multiply roofline microbenchmark on devices[dev_index].  variant 0: independent
+ * IMAD.WIDE.U32 accumulations; 1: IMAD.WIDE.U32.X carry chains; 2: IMAD (32-bit mad.lo); 3: mul.lo +
+ * mul.hi pairs (counted as one product per pair).  Writes 32x32 limb-products per second. */
+int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products_per_s);
+/* Registers per thread / local (spill) bytes / max threads of a kernel: "perm3" | "perm5" | "perm9" |
+ * "merkle" | "sponge". */
+int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
+                      int* max_threads_per_block);
+/* Number of kernel launches issued through this context since creation (bench's gpu_launches). */
+uint64_t hades_launch_count(const hades_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HADES_CUDA_H */
