@@ -1,0 +1,235 @@
+// Host-side derivation (once, inside hades_init) of the constant tables the kernels consume, from the
+// two tables the reference owns: ROUND_CONSTANTS (src/round_constants.rs:29-48) and MDS_MATRIX
+// (src/mds_matrix.rs:18-40).  This is constant preprocessing, not a data path: no state is ever
+// permuted on the host.
+//
+// The 59 partial rounds of `Strategy::perm` (src/strategies.rs:149-151) apply the S-box to the LAST
+// word only (strategies.rs:83-89), so everything else in those rounds is linear and can be
+// re-associated without changing any output (F_p arithmetic is exact):
+//   (1) round-constant pushing: write the state entering partial round q as z_q + d_q with
+//       d_q[last] = 0; the S-box ignores d_q, so d_{q+1} = first W-1 entries of (M d_q + c_{q+1}) and
+//       only the scalar e_{q+1} = (M d_q + c_{q+1})[last] has to be added to the live state.  What is
+//       left after the last partial round (M d_58) merges into the next full round's constants.
+//   (2) sparse factorisation: a dense D = [[A, b], [c^T, d]] (A: (W-1)x(W-1)) factors as
+//       D = S * M'  with  M' = blockdiag(A, 1)  and  S = [[I, b], [c^T A^-1, d]].  M' commutes with the
+//       partial S-box (it fixes the last word), so it migrates into the previous round's matrix:
+//       D_58 = M, D_{q-1} = M'_q * M.  The leftover M'_0 merges into the last of the first four full
+//       rounds (matrix PRE = M'_0 * M, and the first partial ARK becomes M'_0 * c_4).
+// Each partial round then costs 2W-1 field multiplications instead of W^2.
+//
+// Table layout (entries of 4 u64 Montgomery limbs), W = width, F = 8 full rounds, Q = 59:
+//   [0,            F*W)        ARK of the full rounds: rounds 0..3, then c63' = c_63 + M d_58, c_64..c_66
+//   [F*W,          +W*W)       MDS   (dense M, row-major)
+//   [..,           +W*W)       PRE   (dense M'_0 * M, used by full round 3)
+//   [..,           +W)         C4'   (M'_0 * c_4, added to every word before the first partial round)
+//   [..,           +Q*2W)      per partial round q: e_q, d_q, b_q[0..W-2], chat_q[0..W-2]
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+namespace hades_host {
+
+typedef unsigned __int128 u128;
+struct F {
+    uint64_t l[4];
+};
+
+static const uint64_t kMod[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL,
+                                 0x73eda753299d7d48ULL};
+static const uint64_t kInv64 = 0xfffffffeffffffffULL;  // -p^-1 mod 2^64
+static const F kOne = {{0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL,
+                        0x1824b159acc5056fULL}};  // R mod p
+static const F kZero = {{0, 0, 0, 0}};
+
+inline bool geq_mod(const uint64_t a[4], uint64_t top) {
+    if (top) return true;
+    for (int i = 3; i >= 0; i--) {
+        if (a[i] > kMod[i]) return true;
+        if (a[i] < kMod[i]) return false;
+    }
+    return true;
+}
+inline void sub_mod_inplace(uint64_t a[4]) {
+    u128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 t = (u128)a[i] - kMod[i] - bw;
+        a[i] = (uint64_t)t;
+        bw = (t >> 64) & 1;
+    }
+}
+inline F add(const F& a, const F& b) {
+    F r;
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+        c += (u128)a.l[i] + b.l[i];
+        r.l[i] = (uint64_t)c;
+        c >>= 64;
+    }
+    if (geq_mod(r.l, (uint64_t)c)) sub_mod_inplace(r.l);
+    return r;
+}
+inline F neg(const F& a) {
+    bool zero = !(a.l[0] | a.l[1] | a.l[2] | a.l[3]);
+    if (zero) return a;
+    F r;
+    u128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 t = (u128)kMod[i] - a.l[i] - bw;
+        r.l[i] = (uint64_t)t;
+        bw = (t >> 64) & 1;
+    }
+    return r;
+}
+inline F sub(const F& a, const F& b) { return add(a, neg(b)); }
+inline F mul(const F& a, const F& b) {  // Montgomery product a*b/R
+    uint64_t t[9] = {0};
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)a.l[j] * b.l[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * kInv64;
+        c = (u128)m * kMod[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)m * kMod[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    F r = {{t[0], t[1], t[2], t[3]}};
+    if (geq_mod(r.l, t[4])) sub_mod_inplace(r.l);
+    return r;
+}
+inline bool is_zero(const F& a) { return !(a.l[0] | a.l[1] | a.l[2] | a.l[3]); }
+inline F inv(const F& a) {  // a^(p-2), Montgomery domain in and out
+    F r = kOne, base = a;
+    uint64_t e[4] = {kMod[0] - 2, kMod[1], kMod[2], kMod[3]};
+    for (int i = 0; i < 256; i++) {
+        if ((e[i / 64] >> (i % 64)) & 1) r = mul(r, base);
+        base = mul(base, base);
+    }
+    return r;
+}
+
+typedef std::vector<F> Vec;
+typedef std::vector<Vec> Mat;
+
+inline Vec matvec(const Mat& A, const Vec& v) {
+    Vec r(A.size(), kZero);
+    for (size_t i = 0; i < A.size(); i++)
+        for (size_t j = 0; j < v.size(); j++) r[i] = add(r[i], mul(A[i][j], v[j]));
+    return r;
+}
+inline Mat matmul(const Mat& A, const Mat& B) {
+    Mat r(A.size(), Vec(B[0].size(), kZero));
+    for (size_t i = 0; i < A.size(); i++)
+        for (size_t j = 0; j < B[0].size(); j++)
+            for (size_t k = 0; k < B.size(); k++) r[i][j] = add(r[i][j], mul(A[i][k], B[k][j]));
+    return r;
+}
+// Gauss-Jordan; returns false if singular.
+inline bool invert(const Mat& A, Mat& out) {
+    size_t n = A.size();
+    Mat M(n, Vec(2 * n, kZero));
+    for (size_t i = 0; i < n; i++) {
+        for (size_t j = 0; j < n; j++) M[i][j] = A[i][j];
+        M[i][n + i] = kOne;
+    }
+    for (size_t c = 0; c < n; c++) {
+        size_t piv = c;
+        while (piv < n && is_zero(M[piv][c])) piv++;
+        if (piv == n) return false;
+        std::swap(M[c], M[piv]);
+        F iv = inv(M[c][c]);
+        for (auto& x : M[c]) x = mul(x, iv);
+        for (size_t r = 0; r < n; r++) {
+            if (r == c || is_zero(M[r][c])) continue;
+            F f = M[r][c];
+            for (size_t k = 0; k < 2 * n; k++) M[r][k] = sub(M[r][k], mul(f, M[c][k]));
+        }
+    }
+    out.assign(n, Vec(n));
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = 0; j < n; j++) out[i][j] = M[i][n + j];
+    return true;
+}
+
+constexpr int kFull = 8, kPartial = 59, kHalf = 4;
+
+inline size_t table_entries(int W) { return (size_t)kFull * W + 2 * (size_t)W * W + W + (size_t)kPartial * 2 * W; }
+
+// ark: >= 67*W entries, mds: W*W entries (Montgomery limbs).  out: table_entries(W)*4 u64.
+inline bool derive_tables(int W, const uint64_t* ark, const uint64_t* mds, std::vector<uint64_t>& out) {
+    const int t = W - 1;
+    auto getF = [](const uint64_t* p) { F f; for (int i = 0; i < 4; i++) f.l[i] = p[i]; return f; };
+    Mat M(W, Vec(W));
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < W; j++) M[i][j] = getF(mds + (size_t)(i * W + j) * 4);
+    std::vector<Vec> c(kFull + kPartial, Vec(W));
+    for (int r = 0; r < kFull + kPartial; r++)
+        for (int j = 0; j < W; j++) c[r][j] = getF(ark + (size_t)(r * W + j) * 4);
+    // (1) constant pushing, forward
+    Vec d(W, kZero), e(kPartial, kZero);
+    for (int q = 0; q + 1 < kPartial; q++) {
+        Vec u = matvec(M, d);
+        for (int j = 0; j < W; j++) u[j] = add(u[j], c[kHalf + q + 1][j]);
+        e[q + 1] = u[t];
+        d = u;
+        d[t] = kZero;
+    }
+    Vec tail = matvec(M, d);
+    // (2) sparse factorisation, backward
+    struct Sparse { Vec b, chat; F dd; };
+    std::vector<Sparse> sp(kPartial);
+    Mat D = M, Mp;
+    for (int q = kPartial - 1; q >= 0; q--) {
+        Mat A(t, Vec(t)), Ai;
+        for (int i = 0; i < t; i++)
+            for (int j = 0; j < t; j++) A[i][j] = D[i][j];
+        if (!invert(A, Ai)) return false;
+        sp[q].b.resize(t);
+        sp[q].chat.assign(t, kZero);
+        for (int i = 0; i < t; i++) sp[q].b[i] = D[i][t];
+        for (int j = 0; j < t; j++)
+            for (int k = 0; k < t; k++) sp[q].chat[j] = add(sp[q].chat[j], mul(D[t][k], Ai[k][j]));
+        sp[q].dd = D[t][t];
+        Mp.assign(W, Vec(W, kZero));
+        for (int i = 0; i < t; i++)
+            for (int j = 0; j < t; j++) Mp[i][j] = A[i][j];
+        Mp[t][t] = kOne;
+        D = matmul(Mp, M);
+    }
+    Vec c4 = matvec(Mp, c[kHalf]);
+    out.clear();
+    out.reserve(table_entries(W) * 4);
+    auto put = [&](const F& f) { for (int i = 0; i < 4; i++) out.push_back(f.l[i]); };
+    for (int r = 0; r < kHalf; r++)
+        for (int j = 0; j < W; j++) put(c[r][j]);
+    for (int j = 0; j < W; j++) put(add(c[kHalf + kPartial][j], tail[j]));
+    for (int r = kHalf + kPartial + 1; r < kFull + kPartial; r++)
+        for (int j = 0; j < W; j++) put(c[r][j]);
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < W; j++) put(M[i][j]);
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < W; j++) put(D[i][j]);
+    for (int j = 0; j < W; j++) put(c4[j]);
+    for (int q = 0; q < kPartial; q++) {
+        put(e[q]);
+        put(sp[q].dd);
+        for (int i = 0; i < t; i++) put(sp[q].b[i]);
+        for (int i = 0; i < t; i++) put(sp[q].chat[i]);
+    }
+    return out.size() == table_entries(W) * 4;
+}
+
+}  // namespace hades_host
