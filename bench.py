@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", default=None, help="algo,regs kernel variant (default: library default)")
     return ap.parse_args()
 
 
@@ -189,6 +190,9 @@ def run_ours(args):
 
     from hades252_b200 import CudaStrategy
     strat = CudaStrategy([local])
+    if args.variant:
+        algo, regs = (int(x) for x in args.variant.split(","))
+        strat.set_variant(algo, regs)
     n = 1 << args.log2_states
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
@@ -200,9 +204,10 @@ def run_ours(args):
 
     # roofline denominator, measured live on this device
     peaks = {v: strat.imad_peak(v) for v in range(4)}
-    names = {0: "imad_wide", 1: "imad_wide_carry_chain", 2: "imad_lo32", 3: "mul_lo_hi_pair"}
-    p_mul32 = max(peaks[0], peaks[1], peaks[3])  # variants that deliver a full 64-bit product
-    info = strat.kernel_info("perm5")
+    names = {0: "imad_wide_x_carry_chain", 1: "imad_wide_carry_out_only", 2: "imad_lo32_half_product_context_only",
+             3: "imad_lo_plus_imad_hi_pair"}
+    p_mul32 = max(peaks[0], peaks[1], peaks[3])  # forms that deliver a full 64-bit multiply-accumulate
+    info = strat.kernel_info("perm")
 
     # ---- device-resident leg: states generated on device, permuted in place K times -------------
     states = torch.empty(n * WIDTH * 4, dtype=torch.int64, device="cuda")
@@ -296,7 +301,7 @@ def run_ours(args):
                        "l2_policy": "inputs (10.7 GB) larger than L2", "parallelism": f"dp{world} (independent states, no collective)"},
             "roofline": {"bound": "int_mul", "achieved": achieved, "peak": p_mul32 / 1e12, "unit": "Tprod/s",
                          "frac": achieved / (p_mul32 / 1e12), "traffic": None,
-                         "kernel": "perm_batch_kernel<5>", "kernel_ms": kernel_ms,
+                         "kernel": "perm_batch_kernel (width 5)", "variant": args.variant or "default", "kernel_ms": kernel_ms,
                          "algorithmic_products_per_perm": LIMB_PRODUCTS_PER_PERM,
                          "peak_source": "hades_imad_peak live on this device",
                          "peak_variants_Tprod_s": {names[v]: peaks[v] / 1e12 for v in peaks}},

@@ -36,6 +36,7 @@ SIGNATURES = {
     "hades_imad_peak": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "hades_kernel_info": (ctypes.c_int, [ctx_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int),
                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "hades_set_variant": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_int]),
     "hades_launch_count": (ctypes.c_uint64, [ctx_p]),
 }
 

@@ -8,10 +8,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libhades_b200.so")
-SOURCES = ["hades_engine.cu"]
-HEADERS = ["fr.cuh", "hades.cuh", "kernels.cuh", os.path.join("..", "..", "include", "hades_cuda.h")]
+SOURCES = ["hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu"]
+HEADERS = ["fr.cuh", "hades.cuh", "width_impl.cuh", "width_ops.hpp", "util_kernels.cuh", "host_tables.hpp",
+           os.path.join("..", "..", "include", "hades_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def _stale() -> bool:
@@ -22,19 +23,39 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One nvcc -c per translation unit (in parallel), then one link into the shared library."""
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    objdir = os.path.join(HERE, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return src, obj, cmd, res
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
     log = os.path.join(HERE, "lib", "build.log")
     with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout)
-    if verbose or res.returncode:
-        sys.stderr.write(res.stdout)
+        for src, obj, cmd, res in results:
+            f.write(" ".join(cmd) + "\n" + res.stdout + "\n")
+    for src, obj, cmd, res in results:
+        if verbose or res.returncode:
+            sys.stderr.write(res.stdout)
+        if res.returncode:
+            raise RuntimeError(f"nvcc failed on {src} ({res.returncode}); see {log}")
+    link = [nvcc, "-shared", "-cudart", "static", "-o", LIB, *[r[1] for r in results]]
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(log, "a") as f:
+        f.write(" ".join(link) + "\n" + res.stdout)
     if res.returncode:
-        raise RuntimeError(f"nvcc failed ({res.returncode}); see {log}")
+        sys.stderr.write(res.stdout)
+        raise RuntimeError(f"link failed ({res.returncode}); see {log}")
     return LIB
 
 

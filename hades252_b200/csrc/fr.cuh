@@ -51,6 +51,18 @@ struct Fr {
     uint32_t l[8];
 };
 
+// Modulus limbs as MULTIPLICANDS.  On the device they are read from `__constant__` memory so that
+// ptxas sees an opaque uniform operand: with immediates it special-cases p[1] = 0xffffffff into
+// IMAD.HI.U32 + IADD3 and splits many IMAD.WIDE.U32.X into IMAD.X + IMAD.HI.U32.X pairs, which cost
+// 2.0 + 5.1 pipe cycles instead of 4.05 (profiles/r01_microbench_pipe_costs.txt).
+#if !HADES_EMUL
+static __constant__ uint32_t c_modp[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                          0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+HADES_DEV uint32_t modp(int k) { return c_modp[k]; }
+#else
+HADES_DEV uint32_t modp(int k) { return p_limb(k); }
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Chain primitives.  Each is ONE asm statement: the carry flag never lives across statements.
 // ------------------------------------------------------------------------------------------------
@@ -129,16 +141,16 @@ HADES_DEV void redc_even(uint32_t (&acc)[9], uint32_t m) {
 #if !HADES_EMUL
     asm("add.cc.u32 %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, 0;\n\t"
-        "madc.lo.cc.u32 %2, %9, 0xfffe5bfe, %2;\n\t"
-        "madc.hi.cc.u32 %3, %9, 0xfffe5bfe, %3;\n\t"
-        "madc.lo.cc.u32 %4, %9, 0x09a1d805, %4;\n\t"
-        "madc.hi.cc.u32 %5, %9, 0x09a1d805, %5;\n\t"
-        "madc.lo.cc.u32 %6, %9, 0x299d7d48, %6;\n\t"
-        "madc.hi.cc.u32 %7, %9, 0x299d7d48, %7;\n\t"
+        "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, %12, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, %12, %7;\n\t"
         "addc.u32 %8, %8, 0;"
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
           "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
-        : "r"(m));
+        : "r"(m), "r"(modp(2)), "r"(modp(4)), "r"(modp(6)));
 #else
     uint64_t s = (uint64_t)acc[0] + m;
     acc[0] = (uint32_t)s;
@@ -303,7 +315,7 @@ HADES_DEV void dot_step(uint32_t (&E)[9], uint32_t (&O)[9], uint32_t x, int i, V
     for (int j = 0; j < N; j++) cmad4(E, vec(j, 0), vec(j, 2), vec(j, 4), vec(j, 6), sca(j, i));
     // Montgomery step: m = -E[0]; add m*p so that position 0 clears
     uint32_t m = 0u - E[0];
-    cmad4(O, p_limb(1), p_limb(3), p_limb(5), p_limb(7), m);
+    cmad4(O, modp(1), modp(3), modp(5), modp(7), m);
     redc_even(E, m);
 }
 

@@ -72,4 +72,122 @@ HADES_DEV void hades_perm(Fr (&s)[W]) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Optimised schedule: identical outputs, fewer multiplications.
+//
+// The partial rounds apply x^5 to the last word only (strategies.rs:83-89), so the rest of those
+// rounds is linear and is re-associated on the host once (host_tables.hpp): round constants are
+// pushed through the linear layer (only one scalar e_q per round remains) and each dense MDS is
+// factored into a sparse matrix [[I, b], [chat^T, d]] whose dense factor migrates into the previous
+// round.  Per partial round: W-1 single products  w_i += b_i*s  plus one W-term dot product, i.e.
+// 2W-1 field multiplications instead of W^2.  F_p arithmetic is exact and every output is
+// canonical, so the results are bit-identical to `Strategy::perm`.
+//
+// `T` is a table policy:  uint32_t T::tab(int entry, int limb)  over the layout of host_tables.hpp:
+//   [0, 8W) full-round ARK | MDS (W*W) | PRE (W*W) | C4' (W) | 59 x { e, d, b[W-1], chat[W-1] }
+// ------------------------------------------------------------------------------------------------
+template <int W>
+struct OptLayout {
+    static constexpr int kArk = 0;
+    static constexpr int kMds = kFullRounds * W;
+    static constexpr int kPre = kMds + W * W;
+    static constexpr int kC4 = kPre + W * W;
+    static constexpr int kSparse = kC4 + W;
+    static constexpr int kSparseStride = 2 * W;
+    static constexpr int kEntries = kSparse + kPartialRounds * kSparseStride;
+};
+
+template <int W, class T>
+HADES_DEV void add_table_vector(Fr (&s)[W], int base) {
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        Fr c;
+#pragma unroll
+        for (int k = 0; k < 8; k++) c.l[k] = T::tab(base + j, k);
+        fr_add(s[j], s[j], c);
+    }
+}
+
+// full round with a dense matrix stored at table entry `mat`
+template <int W, class T>
+HADES_DEV void full_round_opt(Fr (&s)[W], int ark, int mat) {
+    add_table_vector<W, T>(s, ark);
+#pragma unroll
+    for (int j = 0; j < W; j++) fr_sbox(s[j]);
+    Fr out[W];
+#pragma unroll
+    for (int row = 0; row < W; row++) {
+        uint32_t r[9];
+        dot_mont<W>(
+            r, [&](int j, int k) { return T::tab(mat + row * W + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+        canon<(W <= 6) ? 1 : 2>(out[row], r);
+    }
+#pragma unroll
+    for (int j = 0; j < W; j++) s[j] = out[j];
+}
+
+// one sparse partial round; `base` = table entry of {e, d, b[W-1], chat[W-1]}
+template <int W, class T>
+HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
+    constexpr int t = W - 1;
+    // last word: + e_q, then x^5.  The S-box output stays lazily reduced (< 1.886p < 2^256): it only
+    // feeds products below.
+    {
+        Fr e;
+#pragma unroll
+        for (int k = 0; k < 8; k++) e.l[k] = T::tab(base, k);
+        fr_add(s[t], s[t], e);
+    }
+    Fr y, x2, x4;
+    fr_mul_lazy(x2, s[t], s[t]);
+    fr_mul_lazy(x4, x2, x2);
+    fr_mul_lazy(y, x4, s[t]);
+    // new last word = sum_{j<t} chat_j * w_j + d * y  (uses the OLD w_j)
+    // bound: (t + 1.886) p^2  =>  < p (1 + 0.4528 (t + 1.886)): W=5 -> 3.67p, W=9 -> 5.48p
+    uint32_t r[9];
+    dot_mont<W>(
+        r, [&](int j, int k) { return j < t ? T::tab(base + 2 + t + j, k) : T::tab(base + 1, k); },
+        [&](int j, int i) { return j < t ? s[j].l[i] : y.l[i]; });
+    Fr last;
+    canon<(W <= 5) ? 1 : 2>(last, r);
+    // w_i += b_i * y :  product < 1.854p, plus w_i < p  =>  < 2.854p < 4p
+#pragma unroll
+    for (int i = 0; i < t; i++) {
+        uint32_t q[9];
+        dot_mont<1>(
+            q, [&](int, int k) { return T::tab(base + 2 + i, k); }, [&](int, int limb) { return y.l[limb]; });
+        uint32_t sum[9];
+        uint32_t q8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q8[k] = q[k];
+        uint32_t lo[8];
+        uint32_t c = add8(lo, q8, s[i].l);
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum[k] = lo[k];
+        sum[8] = q[8] + c;
+        canon<1>(s[i], sum);
+    }
+    s[t] = last;
+}
+
+template <int W, class T>
+HADES_DEV void hades_perm_opt(Fr (&s)[W]) {
+    typedef OptLayout<W> L;
+    constexpr int kHalf = kFullRounds / 2;
+#if !HADES_EMUL
+#pragma unroll 1
+#endif
+    for (int f = 0; f < kFullRounds; f++) {
+        full_round_opt<W, T>(s, L::kArk + f * W, (f == kHalf - 1) ? L::kPre : L::kMds);
+        if (f == kHalf - 1) {
+            add_table_vector<W, T>(s, L::kC4);
+#if !HADES_EMUL
+#pragma unroll 1
+#endif
+            for (int q = 0; q < kPartialRounds; q++) partial_round_opt<W, T>(s, L::kSparse + q * L::kSparseStride);
+        }
+    }
+}
+
 }  // namespace hades

@@ -14,12 +14,16 @@
 #include <vector>
 
 #include "../../include/hades_cuda.h"
-#include "kernels.cuh"
+#include "fr.cuh"
+#include "host_tables.hpp"
+#include "util_kernels.cuh"
+#include "width_ops.hpp"
 
 using namespace hades;
 
 namespace {
 
+constexpr int kRounds = 67;                      // 8 full + 59 partial (src/lib.rs:20-27)
 constexpr int kNumBuf = 3;                       // chunk buffers (and streams) per device
 constexpr size_t kChunkBytes = (size_t)96 << 20;  // target bytes per pipeline chunk
 
@@ -36,6 +40,8 @@ thread_local std::string g_init_error;
 
 struct hades_ctx {
     uint32_t width = 0;
+    const WidthOps* ops = nullptr;
+    Variant variant = {1, 0};  // optimised schedule, <=128 registers
     std::vector<DeviceState> devs;
     mutable std::string err;
     uint64_t launches = 0;
@@ -68,39 +74,27 @@ int fail(hades_ctx* ctx, int code, const char* fmt, ...) {
 
 bool valid_dev(const hades_ctx* ctx, int dev_index) { return ctx && dev_index >= 0 && dev_index < (int)ctx->devs.size(); }
 
-int upload_table(hades_ctx* ctx, int ordinal, int key, const void* symbol, const uint64_t* limbs, size_t n_u64) {
+// Tables resident in __constant__ memory per (device ordinal, width): the reference's tables are
+// compile-time constants of the crate, so they are process-wide here as well.
+int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dense, const std::vector<uint64_t>& opt) {
     std::lock_guard<std::mutex> lock(g_tables_mutex);
-    auto it = g_tables.find({ordinal, key});
+    auto it = g_tables.find({ordinal, (int)ctx->width});
     if (it != g_tables.end()) {
-        if (it->second.size() != n_u64 || memcmp(it->second.data(), limbs, n_u64 * 8) != 0)
+        if (it->second != dense)
             return fail(ctx, HADES_ERR_CONSTANTS,
-                        "constant table (device %d, %s) already resident with different contents", ordinal,
-                        key ? "mds" : "ark");
+                        "constant tables for width %u already resident on device %d with different contents", ctx->width, ordinal);
         return HADES_OK;
     }
-    CUDA_TRY(ctx, cudaMemcpyToSymbol(symbol, limbs, n_u64 * 8, 0, cudaMemcpyHostToDevice));
-    g_tables[{ordinal, key}] = std::vector<uint64_t>(limbs, limbs + n_u64);
-    return HADES_OK;
-}
-
-template <int W>
-int launch_perm(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t stream) {
-    if (n == 0) return HADES_OK;
-    size_t blocks = (n + kPermThreads - 1) / kPermThreads;
-    if (blocks > 0x7fffffffULL) return fail(ctx, HADES_ERR_INVALID_ARG, "batch too large for one launch");
-    perm_batch_kernel<W><<<(unsigned)blocks, kPermThreads, 0, stream>>>(reinterpret_cast<uint4*>(d_states), n);
-    ctx->launches++;
-    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, ctx->ops->upload(dense.data(), opt.data()));
+    g_tables[{ordinal, (int)ctx->width}] = dense;
     return HADES_OK;
 }
 
 int launch_perm_w(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t stream) {
-    switch (ctx->width) {
-        case 3: return launch_perm<3>(ctx, d_states, n, stream);
-        case 5: return launch_perm<5>(ctx, d_states, n, stream);
-        case 9: return launch_perm<9>(ctx, d_states, n, stream);
-    }
-    return fail(ctx, HADES_ERR_INVALID_ARG, "unsupported width %u", ctx->width);
+    if (n == 0) return HADES_OK;
+    ctx->launches++;
+    CUDA_TRY(ctx, ctx->ops->launch_perm(ctx->variant, d_states, n, stream));
+    return HADES_OK;
 }
 
 int ensure_chunks(hades_ctx* ctx, DeviceState& d, size_t bytes) {
@@ -124,11 +118,8 @@ int merkle_reduce(hades_ctx* ctx, const uint64_t* d_nodes, size_t n_nodes, int l
     for (int l = 0; l < levels; l++) {
         size_t n_out = n / 4;
         uint64_t* out = (l == levels - 1) ? d_out : ((l & 1) ? bufB : bufA);
-        size_t blocks = (n_out + kPermThreads - 1) / kPermThreads;
-        merkle_level_kernel<<<(unsigned)blocks, kPermThreads, 0, stream>>>(reinterpret_cast<const uint4*>(in),
-                                                                         reinterpret_cast<uint4*>(out), n_out);
         ctx->launches++;
-        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, ctx->ops->launch_merkle_level(ctx->variant, in, out, n_out, stream));
         in = out;
         n = n_out;
     }
@@ -156,7 +147,6 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     if ((size_t)kRounds * width > n_ark)
         return fail(nullptr, HADES_ERR_OUT_OF_CONSTANTS, "Hades252 out of ARK constants: need %zu, got %zu",
                     (size_t)kRounds * width, n_ark);
-    if (n_ark > HADES_N_ROUND_CONSTANTS) n_ark = HADES_N_ROUND_CONSTANTS;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count < 1)
@@ -164,7 +154,15 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
+    ctx->ops = width == 3 ? width_ops_3() : width == 5 ? width_ops_5() : width_ops_9();
+    ctx->variant = Variant{1, width == 3 ? 0 : width == 5 ? 1 : 2};  // spill-free register budgets
+    // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
+    std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
+    dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
     int rc = HADES_OK;
+    if (dense.size() != ctx->ops->dense_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
+    if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops->opt_u64))
+        rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the sparse partial-round tables (singular MDS sub-matrix)");
     for (int g = 0; g < n_dev && rc == HADES_OK; g++) {
         DeviceState d;
         d.ordinal = devices ? devices[g] : g;
@@ -179,10 +177,7 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
         auto step = [&]() -> int {
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
             for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d.streams[b], cudaStreamNonBlocking));
-            int r = upload_table(ctx, d.ordinal, 0, c_ark, ark_limbs, n_ark * 4);
-            if (r) return r;
-            const void* sym = width == 3 ? (const void*)c_mds3 : width == 5 ? (const void*)c_mds5 : (const void*)c_mds9;
-            return upload_table(ctx, d.ordinal, (int)width, sym, mds_limbs, (size_t)width * width * 4);
+            return upload_tables(ctx, d.ordinal, dense, opt);
         };
         rc = step();
     }
@@ -374,11 +369,8 @@ int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elem
     if (!d_offsets || !d_out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     if (((uintptr_t)d_elems | (uintptr_t)d_out) & 15) return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
-    size_t blocks = (n_msgs + kPermThreads - 1) / kPermThreads;
-    sponge_kernel<<<(unsigned)blocks, kPermThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4*>(d_elems), d_offsets, nullptr, reinterpret_cast<uint4*>(d_out), n_msgs);
     ctx->launches++;
-    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, ctx->ops->launch_sponge(ctx->variant, d_elems, d_offsets, nullptr, d_out, n_msgs, (cudaStream_t)stream));
     return HADES_OK;
 }
 
@@ -425,13 +417,10 @@ int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* of
                 CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].elems, elems + offsets[0] * 4, n_elems * 32, cudaMemcpyHostToDevice, d.streams[0]));
             CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].offsets, offsets, (n_msgs + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
             CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].order, dev_order[g].data(), cnt * 4, cudaMemcpyHostToDevice, d.streams[0]));
-            size_t blocks = (cnt + kPermThreads - 1) / kPermThreads;
             // offsets are absolute: bias the element base pointer by offsets[0]
-            const uint4* ebase = reinterpret_cast<const uint4*>(bufs[g].elems) - offsets[0] * 2;
-            sponge_kernel<<<(unsigned)blocks, kPermThreads, 0, d.streams[0]>>>(ebase, bufs[g].offsets, bufs[g].order,
-                                                                             reinterpret_cast<uint4*>(bufs[g].out), cnt);
+            const uint64_t* ebase = bufs[g].elems - offsets[0] * 4;
             ctx->launches++;
-            CUDA_TRY(ctx, cudaGetLastError());
+            CUDA_TRY(ctx, ctx->ops->launch_sponge(ctx->variant, ebase, bufs[g].offsets, bufs[g].order, bufs[g].out, cnt, d.streams[0]));
             if (G == 1) CUDA_TRY(ctx, cudaMemcpyAsync(out, bufs[g].out, n_msgs * 32, cudaMemcpyDeviceToHost, d.streams[0]));
             return HADES_OK;
         };
@@ -497,7 +486,7 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     const int threads = 256, blocks = 148 * 8;
     uint32_t *d_in = nullptr, *d_out = nullptr;
-    std::vector<uint32_t> h(128);
+    std::vector<uint32_t> h(64 * 32);
     for (size_t i = 0; i < h.size(); i++) h[i] = (uint32_t)splitmix64(i + 1) | 1u;
     CUDA_TRY(ctx, cudaMalloc(&d_in, h.size() * 4));
     CUDA_TRY(ctx, cudaMalloc(&d_out, (size_t)threads * blocks * 4));
@@ -516,7 +505,7 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
     };
     launch(64);  // warm-up
     CUDA_TRY(ctx, cudaDeviceSynchronize());
-    const int iters = 4096;
+    const int iters = 1024;
     double best = 0;
     for (int rep = 0; rep < 3; rep++) {
         CUDA_TRY(ctx, cudaEventRecord(e0));
@@ -525,8 +514,7 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
         CUDA_TRY(ctx, cudaEventSynchronize(e1));
         float ms = 0;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
-        // per thread and iteration: 8 unrolled steps x 8 products
-        double prods = (double)threads * blocks * (double)iters * 8.0 * 8.0;
+        double prods = (double)threads * blocks * (double)iters * (variant == 0 ? kPeakProductsPerIterV0 : kPeakProductsPerIterV123);
         best = std::max(best, prods / (ms * 1e-3));
     }
     CUDA_TRY(ctx, cudaGetLastError());
@@ -539,19 +527,20 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
 int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
                       int* max_threads_per_block) {
     if (!ctx || !kernel) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
-    const void* fn = nullptr;
-    if (!strcmp(kernel, "perm3")) fn = (const void*)perm_batch_kernel<3>;
-    else if (!strcmp(kernel, "perm5")) fn = (const void*)perm_batch_kernel<5>;
-    else if (!strcmp(kernel, "perm9")) fn = (const void*)perm_batch_kernel<9>;
-    else if (!strcmp(kernel, "merkle")) fn = (const void*)merkle_level_kernel;
-    else if (!strcmp(kernel, "sponge")) fn = (const void*)sponge_kernel;
-    else return fail(ctx, HADES_ERR_INVALID_ARG, "unknown kernel '%s'", kernel);
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
     cudaFuncAttributes a;
-    CUDA_TRY(ctx, cudaFuncGetAttributes(&a, fn));
+    cudaError_t e = ctx->ops->func_attributes(kernel, ctx->variant, &a);
+    if (e == cudaErrorInvalidValue) return fail(ctx, HADES_ERR_INVALID_ARG, "unknown kernel '%s' for width %u", kernel, ctx->width);
+    CUDA_TRY(ctx, e);
     if (regs_per_thread) *regs_per_thread = a.numRegs;
     if (local_bytes) *local_bytes = (int)a.localSizeBytes;
     if (max_threads_per_block) *max_threads_per_block = a.maxThreadsPerBlock;
+    return HADES_OK;
+}
+
+int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
+    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 2) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
+    ctx->variant = Variant{algo, regs};
     return HADES_OK;
 }
 

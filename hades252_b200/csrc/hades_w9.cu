@@ -1,0 +1,6 @@
+// Width-9 kernels of the Hades252 engine (own translation unit = own 64 KB __constant__ bank).
+#define HADES_W 9
+#include "width_impl.cuh"
+namespace hades {
+const WidthOps* width_ops_9() { return &kOps; }
+}  // namespace hades

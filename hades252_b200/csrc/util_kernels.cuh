@@ -1,0 +1,131 @@
+// Measurement helpers: synthetic inputs, digests and the integer-multiply roofline microbenchmark.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fr.cuh"
+
+namespace hades {
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+// element e (global index), limb l = splitmix64(seed + 4e + l), top limb masked to 62 bits
+__global__ void gen_elems_kernel(uint64_t* __restrict__ out, uint64_t first_elem, size_t n_elems, uint64_t seed) {
+    size_t n_limbs = n_elems * 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_limbs; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t v = splitmix64(seed + first_elem * 4 + i);
+        out[i] = ((i & 3) == 3) ? (v & 0x3fffffffffffffffULL) : v;
+    }
+}
+
+__global__ void digest_kernel(const uint64_t* __restrict__ limbs, uint64_t first_limb, size_t n_limbs,
+                              unsigned long long* __restrict__ digest) {
+    uint64_t x = 0, s = 0, x2 = 0, s2 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_limbs; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t v = limbs[i];
+        uint64_t h = splitmix64(v ^ splitmix64(first_limb + i));
+        x ^= h; s += h; x2 ^= v; s2 += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        x2 ^= __shfl_xor_sync(0xffffffffu, x2, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicXor(digest + 0, (unsigned long long)x);
+        atomicAdd(digest + 1, (unsigned long long)s);
+        atomicXor(digest + 2, (unsigned long long)x2);
+        atomicAdd(digest + 3, (unsigned long long)s2);
+    }
+}
+
+// ---- integer-multiply roofline microbenchmark --------------------------------------------------------
+// 8 independent accumulators per thread, 8 unrolled steps per loop iteration; multiplicands come from
+// the neighbouring accumulator so nothing is loop-invariant or warp-uniform (ptxas otherwise hoists the
+// product and the loop degenerates into adds -- see tools/microbench.cu, which validates these forms and
+// whose output is profiles/r01_microbench_pipe_costs.txt).  Products per thread per iteration: 8*8*P.
+//   variant 0: 4-link carry chains (IMAD.WIDE.U32.X carry-in + carry-out), the production idiom; P = 4
+//   variant 1: IMAD.WIDE.U32 with carry-out only + IADD3.X;                                      P = 1
+//   variant 2: IMAD (32-bit low half only -- NOT a full product, context only);                  P = 1
+//   variant 3: IMAD + IMAD.HI.U32 pair per product;                                              P = 1
+constexpr int kPeakIlp = 8;
+template <int VARIANT>
+__global__ void __launch_bounds__(256) imad_peak_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                        int iters) {
+    const uint32_t* my = in + (threadIdx.x & 63) * 32;
+    uint32_t a = my[30], b = my[31], r = 0;
+    if (VARIANT == 0) {
+        uint32_t e[kPeakIlp][9];
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++)
+#pragma unroll
+            for (int q = 0; q < 9; q++) e[k][q] = my[(k + q) & 31];
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < kPeakIlp; k++) cmad4(e[k], a, b, a ^ 0x5555u, b ^ 0x3333u, e[(k + 1) & 7][1]);
+        }
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++)
+#pragma unroll
+            for (int q = 0; q < 9; q++) r ^= e[k][q];
+    } else if (VARIANT == 1) {
+        uint32_t lo[kPeakIlp], hi[kPeakIlp], t[kPeakIlp];
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++) { lo[k] = my[k]; hi[k] = my[8 + k]; t[k] = 0; }
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < kPeakIlp; k++)
+                    asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                                 : "+r"(lo[k]), "+r"(hi[k]), "+r"(t[k]) : "r"(hi[(k + 1) & 7]), "r"(b));
+        }
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++) r ^= lo[k] ^ hi[k] ^ t[k];
+    } else if (VARIANT == 2) {
+        uint32_t acc[kPeakIlp];
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++) acc[k] = my[k];
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < kPeakIlp; k++)
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(acc[(k + 1) & 7]), "r"(b));
+        }
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++) r ^= acc[k];
+    } else {
+        uint32_t lo[kPeakIlp], hi[kPeakIlp];
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++) { lo[k] = my[k]; hi[k] = my[8 + k]; }
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < kPeakIlp; k++)
+                    asm volatile("mad.lo.u32 %0, %2, %3, %0;\n\tmad.hi.u32 %1, %2, %3, %1;"
+                                 : "+r"(lo[k]), "+r"(hi[k]) : "r"(hi[(k + 1) & 7]), "r"(b));
+        }
+#pragma unroll
+        for (int k = 0; k < kPeakIlp; k++) r ^= lo[k] ^ hi[k];
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r ^ a;
+}
+constexpr double kPeakProductsPerIterV0 = 8.0 * 8.0 * 4.0;
+constexpr double kPeakProductsPerIterV123 = 8.0 * 8.0;
+
+}  // namespace hades

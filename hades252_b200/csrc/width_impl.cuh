@@ -1,0 +1,213 @@
+// Kernels for ONE permutation width (HADES_W), included by hades_w{3,5,9}.cu.  One thread owns one
+// width-W state (or one Merkle node / one sponge message) and keeps it in registers across all 67
+// rounds.  Memory traffic is 2*32*W bytes per permutation (320 B at W=5) against ~1e5 integer
+// multiplies, so these kernels are bound by the integer-multiply pipe, not by HBM.
+#pragma once
+#ifndef HADES_W
+#error "define HADES_W before including width_impl.cuh"
+#endif
+#include <string.h>
+
+#include "hades.cuh"
+#include "width_ops.hpp"
+
+namespace hades {
+namespace {
+
+constexpr int W = HADES_W;
+typedef OptLayout<W> Layout;
+constexpr int kDenseEntries = kRounds * W + W * W;
+
+// ---- constant tables of this width (uploaded once per device by hades_init) ----------------------
+// dense: ROUND_CONSTANTS[0 .. 67W) (src/round_constants.rs:29-48) then MDS_MATRIX row-major
+//        (src/mds_matrix.rs:18-40); opt: the derived layout of host_tables.hpp.  8 u32 limbs each.
+__constant__ uint32_t c_dense[kDenseEntries * 8];
+__constant__ uint32_t c_opt[Layout::kEntries * 8];
+
+struct DenseConsts {
+    static __device__ __forceinline__ uint32_t ark(int idx, int k) { return c_dense[idx * 8 + k]; }
+    static __device__ __forceinline__ uint32_t mds(int r, int c, int k) { return c_dense[(kRounds * W + r * W + c) * 8 + k]; }
+};
+struct OptTab {
+    static __device__ __forceinline__ uint32_t tab(int entry, int k) { return c_opt[entry * 8 + k]; }
+};
+
+template <int ALGO>
+__device__ __forceinline__ void permute(Fr (&s)[W]) {
+    if constexpr (ALGO == 0) hades_perm<W, DenseConsts>(s);
+    else hades_perm_opt<W, OptTab>(s);
+}
+
+// 32-byte element <-> registers through two 128-bit accesses (pointers are 16-byte aligned).
+__device__ __forceinline__ void fr_load(Fr& x, const uint4* p) {
+    uint4 a = p[0], b = p[1];
+    x.l[0] = a.x; x.l[1] = a.y; x.l[2] = a.z; x.l[3] = a.w;
+    x.l[4] = b.x; x.l[5] = b.y; x.l[6] = b.z; x.l[7] = b.w;
+}
+__device__ __forceinline__ void fr_store(uint4* p, const Fr& x) {
+    p[0] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+    p[1] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+}
+
+// ---- perm_batch: `Strategy::perm` (strategies.rs:140) over n independent states, in place ---------
+template <int ALGO, int MINB>
+__global__ void __launch_bounds__(kPermThreads, MINB) perm_batch_kernel(uint4* __restrict__ states, size_t n) {
+    size_t i = (size_t)blockIdx.x * kPermThreads + threadIdx.x;
+    if (i >= n) return;
+    uint4* p = states + i * (2 * W);
+    Fr s[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) fr_load(s[j], p + 2 * j);
+    permute<ALGO>(s);
+#pragma unroll
+    for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
+}
+
+#if HADES_W == 5
+// Montgomery forms of the two small constants the compositions need (checked in tests).
+__device__ __forceinline__ void fr_set_one(Fr& x) {  // 1 * R mod p
+    const uint32_t v[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                           0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+#pragma unroll
+    for (int k = 0; k < 8; k++) x.l[k] = v[k];
+}
+__device__ __forceinline__ void fr_set_fifteen(Fr& x) {  // 15 * R mod p (Merkle bitmask 0b1111)
+    const uint32_t v[8] = {0xffffffdfu, 0x00000020u, 0x00362421u, 0x348ddb9du,
+                           0xc2232750u, 0x658b26f6u, 0xa2b2d9b1u, 0x0e5d6e47u};
+#pragma unroll
+    for (int k = 0; k < 8; k++) x.l[k] = v[k];
+}
+__device__ __forceinline__ void fr_set_zero(Fr& x) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) x.l[k] = 0;
+}
+
+// ---- merkle level: out[i] = perm([15, in[4i], in[4i+1], in[4i+2], in[4i+3]])[1] ---------------------
+template <int ALGO, int MINB>
+__global__ void __launch_bounds__(kPermThreads, MINB)
+merkle_level_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out) {
+    size_t i = (size_t)blockIdx.x * kPermThreads + threadIdx.x;
+    if (i >= n_out) return;
+    Fr s[5];
+    fr_set_fifteen(s[0]);
+    const uint4* p = in + i * 8;  // 4 children = 128 contiguous bytes
+#pragma unroll
+    for (int j = 0; j < 4; j++) fr_load(s[1 + j], p + 2 * j);
+    permute<ALGO>(s);
+    fr_store(out + i * 2, s[1]);
+}
+
+// ---- sponge: rate 4 / capacity 1, one message per thread (CSR offsets) ------------------------------
+// `order` (optional) maps thread -> message so that a warp works on messages of equal block count.
+template <int ALGO, int MINB>
+__global__ void __launch_bounds__(kPermThreads, MINB)
+sponge_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offsets,
+              const uint32_t* __restrict__ order, uint4* __restrict__ out, size_t n_threads) {
+    size_t t = (size_t)blockIdx.x * kPermThreads + threadIdx.x;
+    if (t >= n_threads) return;
+    size_t m = order ? order[t] : t;
+    uint64_t b = offsets[m], e = offsets[m + 1];
+    Fr s[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) fr_set_zero(s[j]);
+    bool padded = false;
+#pragma unroll 1
+    while (!padded) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            Fr x;
+            bool add = true;
+            if (b < e) {
+                fr_load(x, elems + b * 2);
+                b++;
+            } else if (!padded) {
+                fr_set_one(x);
+                padded = true;
+            } else {
+                add = false;
+            }
+            if (add) fr_add(s[1 + k], s[1 + k], x);
+        }
+        permute<ALGO>(s);
+    }
+    fr_store(out + m * 2, s[1]);
+}
+#endif  // HADES_W == 5
+
+// ---- host-side launchers ---------------------------------------------------------------------------
+cudaError_t upload(const uint64_t* dense, const uint64_t* opt) {
+    cudaError_t e = cudaMemcpyToSymbol(c_dense, dense, sizeof(c_dense), 0, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_opt, opt, sizeof(c_opt), 0, cudaMemcpyHostToDevice);
+}
+
+// regs: 0 -> minBlocks 4 (<=128 registers), 1 -> 3 (<=168), 2 -> 2 (<=255)
+#define HADES_DISPATCH(KERNEL, v, ...)                                                   \
+    do {                                                                                 \
+        const int key_ = (v).algo * 3 + (v).regs;                                        \
+        switch (key_) {                                                                  \
+            case 0: KERNEL<0, 4> __VA_ARGS__; break;                                     \
+            case 1: KERNEL<0, 3> __VA_ARGS__; break;                                     \
+            case 2: KERNEL<0, 2> __VA_ARGS__; break;                                     \
+            case 3: KERNEL<1, 4> __VA_ARGS__; break;                                     \
+            case 4: KERNEL<1, 3> __VA_ARGS__; break;                                     \
+            default: KERNEL<1, 2> __VA_ARGS__; break;                                    \
+        }                                                                                \
+    } while (0)
+
+cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + kPermThreads - 1) / kPermThreads;
+    if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
+    HADES_DISPATCH(perm_batch_kernel, v, <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<uint4*>(d_states), n));
+    return cudaGetLastError();
+}
+
+#if HADES_W == 5
+cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s) {
+    if (n_out == 0) return cudaSuccess;
+    size_t blocks = (n_out + kPermThreads - 1) / kPermThreads;
+    if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
+    HADES_DISPATCH(merkle_level_kernel, v,
+                   <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out));
+    return cudaGetLastError();
+}
+cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
+                          uint64_t* d_out, size_t n_threads, cudaStream_t s) {
+    if (n_threads == 0) return cudaSuccess;
+    size_t blocks = (n_threads + kPermThreads - 1) / kPermThreads;
+    if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
+    HADES_DISPATCH(sponge_kernel, v,
+                   <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_elems), d_offsets, d_order,
+                                                             reinterpret_cast<uint4*>(d_out), n_threads));
+    return cudaGetLastError();
+}
+#endif
+
+#define HADES_ATTR(KERNEL, v, out)                                                       \
+    ((v).algo * 3 + (v).regs == 0   ? cudaFuncGetAttributes(out, KERNEL<0, 4>)           \
+     : (v).algo * 3 + (v).regs == 1 ? cudaFuncGetAttributes(out, KERNEL<0, 3>)           \
+     : (v).algo * 3 + (v).regs == 2 ? cudaFuncGetAttributes(out, KERNEL<0, 2>)           \
+     : (v).algo * 3 + (v).regs == 3 ? cudaFuncGetAttributes(out, KERNEL<1, 4>)           \
+     : (v).algo * 3 + (v).regs == 4 ? cudaFuncGetAttributes(out, KERNEL<1, 3>)           \
+                                    : cudaFuncGetAttributes(out, KERNEL<1, 2>))
+
+cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
+    if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);
+#if HADES_W == 5
+    if (!strcmp(kernel, "merkle")) return HADES_ATTR(merkle_level_kernel, v, out);
+    if (!strcmp(kernel, "sponge")) return HADES_ATTR(sponge_kernel, v, out);
+#endif
+    return cudaErrorInvalidValue;
+}
+
+const WidthOps kOps = {W, (size_t)kDenseEntries * 4, (size_t)Layout::kEntries * 4, upload, launch_perm,
+#if HADES_W == 5
+                       launch_merkle_level, launch_sponge,
+#else
+                       nullptr, nullptr,
+#endif
+                       func_attributes};
+
+}  // namespace
+}  // namespace hades

@@ -1,0 +1,38 @@
+// Interface between the engine (C ABI, hades_engine.cu) and the per-width kernel translation units
+// (hades_w3.cu / hades_w5.cu / hades_w9.cu).  Each width is its own TU because every TU owns a
+// separate 64 KB `__constant__` bank: the width-9 tables alone need 61 KB.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace hades {
+
+// Kernel variants (runtime-selectable so that bench/tests can A/B them; all bit-identical):
+//   algo 0 = dense schedule (reference round structure, one lazily reduced dot product per MDS row)
+//   algo 1 = optimised schedule (sparse partial rounds, host_tables.hpp)
+//   regs 0 = __launch_bounds__(128, 4) (<=128 registers), 1 = (128, 3) (<=168), 2 = (128, 2) (<=255)
+struct Variant {
+    int algo;
+    int regs;
+};
+constexpr int kPermThreads = 128;
+
+struct WidthOps {
+    int width;
+    size_t dense_u64;  // (67*W + W*W) * 4
+    size_t opt_u64;    // OptLayout<W>::kEntries * 4
+    cudaError_t (*upload)(const uint64_t* dense, const uint64_t* opt);  // to the CURRENT device
+    cudaError_t (*launch_perm)(Variant v, uint64_t* d_states, size_t n, cudaStream_t s);
+    // width 5 only (nullptr otherwise)
+    cudaError_t (*launch_merkle_level)(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s);
+    cudaError_t (*launch_sponge)(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
+                                 uint64_t* d_out, size_t n_threads, cudaStream_t s);
+    cudaError_t (*func_attributes)(const char* kernel, Variant v, cudaFuncAttributes* out);
+};
+
+const WidthOps* width_ops_3();
+const WidthOps* width_ops_5();
+const WidthOps* width_ops_9();
+
+}  // namespace hades

@@ -172,6 +172,10 @@ class CudaStrategy(Strategy):
                                                 ctypes.byref(thr)))
         return {"regs_per_thread": regs.value, "local_bytes": local.value, "max_threads_per_block": thr.value}
 
+    def set_variant(self, algo: int = 1, regs: int = 0) -> None:
+        """Kernel variant (bit-identical results): algo 0 dense / 1 sparse partial rounds; regs 0 <=128, 1 <=168."""
+        self._check(self._lib.hades_set_variant(self._ctx, algo, regs))
+
     def host_register(self, ptr: int, nbytes: int) -> None:
         self._check(self._lib.hades_host_register(self._ctx, ptr, nbytes))
 

@@ -128,14 +128,19 @@ int hades_gen_elems_dev(hades_ctx* ctx, int dev_index, uint64_t* d_out, uint64_t
  * [0] ^= H, [1] += H, [2] ^= limb, [3] += limb, H = splitmix64(limb ^ splitmix64(first_limb + i)). */
 int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uint64_t first_limb, size_t n_limbs,
                      uint64_t* d_digest, void* stream);
-/* Integer-multiply roofline microbenchmark on devices[dev_index].  variant 0: independent
- * IMAD.WIDE.U32 accumulations; 1: IMAD.WIDE.U32.X carry chains; 2: IMAD (32-bit mad.lo); 3: mul.lo +
- * mul.hi pairs (counted as one product per pair).  Writes 32x32 limb-products per second. */
+/* Integer-multiply roofline microbenchmark on devices[dev_index]: 32x32->64 multiply-accumulates per
+ * second.  variant 0: IMAD.WIDE.U32.X carry chains (the production idiom); 1: IMAD.WIDE.U32 with
+ * carry-out only; 2: IMAD 32-bit low half only (context: not a full product); 3: IMAD + IMAD.HI.U32
+ * pair per product.  Instruction forms validated in tools/microbench.cu. */
 int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products_per_s);
-/* Registers per thread / local (spill) bytes / max threads of a kernel: "perm3" | "perm5" | "perm9" |
- * "merkle" | "sponge". */
+/* Registers per thread / local (spill) bytes / max threads per block of the context's current kernel
+ * variant: kernel = "perm" | "merkle" | "sponge" (the last two for width 5). */
 int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
                       int* max_threads_per_block);
+/* Select the kernel variant (all bit-identical): algo 0 = dense schedule (the reference's round
+ * structure), 1 = optimised schedule (sparse partial rounds; default); regs 0/1/2 = at most 128/168/255
+ * registers per thread (default: the smallest spill-free budget for the width). */
+int hades_set_variant(hades_ctx* ctx, int algo, int regs);
 /* Number of kernel launches issued through this context since creation (bench's gpu_launches). */
 uint64_t hades_launch_count(const hades_ctx* ctx);
 

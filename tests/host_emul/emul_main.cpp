@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "../../hades252_b200/csrc/hades.cuh"
+#include "../../hades252_b200/csrc/host_tables.hpp"
 
 extern "C" {
 void oracle_fr_mul(const uint64_t*, const uint64_t*, uint64_t*);
@@ -19,6 +20,12 @@ template <int W>
 struct HostConsts {
     static uint32_t ark(int idx, int k) { return (uint32_t)(g_ark[idx * 4 + k / 2] >> (32 * (k & 1))); }
     static uint32_t mds(int r, int c, int k) { return (uint32_t)(g_mds[W][(r * W + c) * 4 + k / 2] >> (32 * (k & 1))); }
+};
+
+static std::vector<uint64_t> g_opt[10];
+template <int W>
+struct HostTab {
+    static uint32_t tab(int entry, int k) { return (uint32_t)(g_opt[W][(size_t)entry * 4 + k / 2] >> (32 * (k & 1))); }
 };
 
 static uint64_t rng_state = 0x1234567;
@@ -47,11 +54,16 @@ static int check_perm(int iters) {
         for (int j = 0; j < W; j++) rand_fr(st + 4 * j, it < 40 ? (it + j) % 5 : 0);
         hades::Fr s[W];
         for (int j = 0; j < W; j++) to32(s[j], st + 4 * j);
+        hades::Fr s2[W];
+        for (int j = 0; j < W; j++) s2[j] = s[j];
         hades::hades_perm<W, HostConsts<W>>(s);
+        hades::hades_perm_opt<W, HostTab<W>>(s2);
         oracle_perm(st, W, g_ark.data(), g_mds[W].data());
         for (int j = 0; j < W; j++) {
             uint64_t got[4]; to64(got, s[j]);
             if (memcmp(got, st + 4 * j, 32)) { printf("perm W=%d mismatch iter %d word %d\n", W, it, j); return 1; }
+            to64(got, s2[j]);
+            if (memcmp(got, st + 4 * j, 32)) { printf("perm_opt W=%d mismatch iter %d word %d\n", W, it, j); return 1; }
         }
     }
     return 0;
@@ -65,6 +77,17 @@ int main(int argc, char** argv) {
     if (fread(g_ark.data(), 8, 960 * 4, f) != 960 * 4) return 2;
     for (int w : {3, 5, 9}) { g_mds[w].resize(w * w * 4); if (fread(g_mds[w].data(), 8, w * w * 4, f) != (size_t)w * w * 4) return 2; }
     fclose(f);
+    for (int w : {3, 5, 9}) {
+        if (!hades_host::derive_tables(w, g_ark.data(), g_mds[w].data(), g_opt[w])) { printf("derive_tables(%d) failed\n", w); return 1; }
+        if (g_opt[w].size() != (size_t)hades::OptLayout<3>::kEntries * 0 + hades_host::table_entries(w) * 4) return 1;
+    }
+    if (hades_host::table_entries(5) != (size_t)hades::OptLayout<5>::kEntries || hades_host::table_entries(9) != (size_t)hades::OptLayout<9>::kEntries ||
+        hades_host::table_entries(3) != (size_t)hades::OptLayout<3>::kEntries) { printf("layout mismatch\n"); return 1; }
+    if (argc > 2) {  // dump the derived tables for the Python cross-check
+        FILE* o = fopen(argv[2], "wb");
+        for (int w : {3, 5, 9}) fwrite(g_opt[w].data(), 8, g_opt[w].size(), o);
+        fclose(o);
+    }
     // field ops
     for (int it = 0; it < 200000; it++) {
         uint64_t a[4], b[4], want[4], got[4];

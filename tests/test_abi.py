@@ -100,7 +100,7 @@ def test_product_constants_match_reference_loader_semantics():
 def test_device_small_constants():
     """Montgomery forms of 1 and 15 hard-coded in kernels.cuh."""
     from oracle import hades_ref as H
-    src = open(os.path.join(ROOT, "hades252_b200", "csrc", "kernels.cuh")).read()
+    src = open(os.path.join(ROOT, "hades252_b200", "csrc", "width_impl.cuh")).read()
     for name, val in (("fr_set_one", 1), ("fr_set_fifteen", 15)):
         body = src[src.index(name):]
         words = re.findall(r"0x([0-9a-f]{8})u", body)[:8]

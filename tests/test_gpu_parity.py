@@ -21,9 +21,44 @@ def H():
 
 
 def test_extension_loaded_and_kernels_spill_free(cuda_strategy):
-    info = cuda_strategy.kernel_info("perm5")
+    info = cuda_strategy.kernel_info("perm")
     assert info["regs_per_thread"] > 0
     print("perm5", info, "merkle", cuda_strategy.kernel_info("merkle"), "sponge", cuda_strategy.kernel_info("sponge"))
+
+
+@pytest.mark.parametrize("algo,regs", [(0, 0), (0, 1), (1, 0), (1, 1), (1, 2)])
+def test_all_kernel_variants_bit_identical(oracle, algo, regs):
+    """dense schedule (reference round structure) vs sparse-partial-round schedule, all register
+    budgets: same bits as the oracle, for perm, merkle and sponge."""
+    from hades252_b200 import CudaStrategy
+    n = 3000
+    s = oracle.gen_elems(321, 5 * n).reshape(n, 5, 4)
+    want = oracle.perm_batch(s)
+    with CudaStrategy([0]) as strat:
+        strat.set_variant(algo, regs)
+        got = s.copy()
+        strat.perm_batch(got)
+        assert np.array_equal(got, want)
+        leaves = oracle.gen_elems(77, 4 ** 5)
+        assert np.array_equal(strat.merkle_root(leaves), oracle.merkle_root(leaves))
+        lens = np.arange(200) % 13
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        elems = oracle.gen_elems(5, int(offsets[-1]))
+        assert np.array_equal(strat.sponge_batch(elems, offsets), oracle.sponge_batch(elems, offsets))
+        print(algo, regs, strat.kernel_info("perm"))
+
+
+@pytest.mark.parametrize("w", [3, 9])
+@pytest.mark.parametrize("algo", [0, 1])
+def test_other_widths_both_schedules(oracle, w, algo):
+    from hades252_b200 import CudaStrategy
+    n = 2000
+    s = oracle.gen_elems(55, w * n).reshape(n, w, 4)
+    with CudaStrategy([0], width=w) as strat:
+        strat.set_variant(algo, 2 if w == 9 else 0)
+        got = s.copy()
+        strat.perm_batch(got)
+    assert np.array_equal(got, oracle.perm_batch(s, w))
 
 
 def test_golden_vectors(cuda_strategy, golden):
