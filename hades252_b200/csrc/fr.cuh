@@ -55,10 +55,17 @@ struct Fr {
 // ptxas sees an opaque uniform operand: with immediates it special-cases p[1] = 0xffffffff into
 // IMAD.HI.U32 + IADD3 and splits many IMAD.WIDE.U32.X into IMAD.X + IMAD.HI.U32.X pairs, which cost
 // 2.0 + 5.1 pipe cycles instead of 4.05 (profiles/r01_microbench_pipe_costs.txt).
+// Deliberately NOT statically initialised (an initialiser gets folded back into immediates): every
+// translation unit that multiplies by the modulus uploads it once with upload_modulus().
 #if !HADES_EMUL
-static __constant__ uint32_t c_modp[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
-                                          0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+static __constant__ uint32_t c_modp[8];
 HADES_DEV uint32_t modp(int k) { return c_modp[k]; }
+#if defined(__CUDACC__)
+static inline cudaError_t upload_modulus() {
+    const uint32_t p[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    return cudaMemcpyToSymbol(c_modp, p, sizeof(p), 0, cudaMemcpyHostToDevice);
+}
+#endif
 #else
 HADES_DEV uint32_t modp(int k) { return p_limb(k); }
 #endif
@@ -313,8 +320,11 @@ HADES_DEV void dot_step(uint32_t (&E)[9], uint32_t (&O)[9], uint32_t x, int i, V
     // even limbs -> E (positions 0..7)
 #pragma unroll
     for (int j = 0; j < N; j++) cmad4(E, vec(j, 0), vec(j, 2), vec(j, 4), vec(j, 6), sca(j, i));
-    // Montgomery step: m = -E[0]; add m*p so that position 0 clears
-    uint32_t m = 0u - E[0];
+    // Montgomery step: m = -E[0] (since -p^-1 = -1 mod 2^32); add m*p so that position 0 clears.
+    // Written as (E0 ^ p[1]) + p[0] = ~E0 + 1 with the two limbs read from constant memory: if ptxas
+    // can prove m == -E0 it rewrites every m*p[k] product into IMAD.X + IMAD.HI.U32.X pairs
+    // (7.1 pipe cycles instead of 4.05).
+    uint32_t m = (E[0] ^ modp(1)) + modp(0);
     cmad4(O, modp(1), modp(3), modp(5), modp(7), m);
     redc_even(E, m);
 }

@@ -109,19 +109,51 @@ HADES_DEV void add_table_vector(Fr (&s)[W], int base) {
     }
 }
 
+// Code-size discipline.  The kernels are bound by the integer-multiply pipe, and the profile of the
+// fully unrolled version showed `no_instruction` stalls: its partial-round loop body was 42 KB of SASS,
+// beyond the instruction cache.  So the per-word work is written as REAL loops over a rotating register
+// file: each trip works on word 0 and then rotates the words by one (plain register moves on the
+// otherwise idle ALU pipe); the loop counter only selects a (warp-uniform) constant-table offset.
+#if HADES_EMUL
+#define HADES_NO_UNROLL
+#else
+#define HADES_NO_UNROLL _Pragma("unroll 1")
+#endif
+
+template <int N>
+HADES_DEV void rotate_in(Fr (&s)[N], const Fr& incoming) {  // s <- (s[1], ..., s[N-1], incoming)
+    Fr tmp = incoming;
+#pragma unroll
+    for (int k = 0; k + 1 < N; k++) s[k] = s[k + 1];
+    s[N - 1] = tmp;
+}
+
 // full round with a dense matrix stored at table entry `mat`
 template <int W, class T>
 HADES_DEV void full_round_opt(Fr (&s)[W], int ark, int mat) {
-    add_table_vector<W, T>(s, ark);
+    // ARK + S-box on every word: W trips of (add constant, x^5) on word 0, rotating
+    HADES_NO_UNROLL
+    for (int j = 0; j < W; j++) {
+        Fr c, x = s[0];
 #pragma unroll
-    for (int j = 0; j < W; j++) fr_sbox(s[j]);
+        for (int k = 0; k < 8; k++) c.l[k] = T::tab(ark + j, k);
+        fr_add(x, x, c);
+        fr_sbox(x);
+        rotate_in<W>(s, x);
+    }
+    // MDS: one lazily reduced W-term dot product per row, rows pushed into a rotating output file
     Fr out[W];
 #pragma unroll
+    for (int j = 0; j < W; j++) out[j] = s[j];  // placeholder values, all W get overwritten
+    HADES_NO_UNROLL
     for (int row = 0; row < W; row++) {
         uint32_t r[9];
+        const int base = mat + row * W;
         dot_mont<W>(
-            r, [&](int j, int k) { return T::tab(mat + row * W + j, k); }, [&](int j, int i) { return s[j].l[i]; });
-        canon<(W <= 6) ? 1 : 2>(out[row], r);
+            r, [&](int j, int k) { return T::tab(base + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+        Fr res;
+        canon<(W <= 6) ? 1 : 2>(res, r);
+        rotate_in<W>(out, res);
     }
 #pragma unroll
     for (int j = 0; j < W; j++) s[j] = out[j];
@@ -145,30 +177,37 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
     fr_mul_lazy(y, x4, s[t]);
     // new last word = sum_{j<t} chat_j * w_j + d * y  (uses the OLD w_j)
     // bound: (t + 1.886) p^2  =>  < p (1 + 0.4528 (t + 1.886)): W=5 -> 3.67p, W=9 -> 5.48p
-    uint32_t r[9];
-    dot_mont<W>(
-        r, [&](int j, int k) { return j < t ? T::tab(base + 2 + t + j, k) : T::tab(base + 1, k); },
-        [&](int j, int i) { return j < t ? s[j].l[i] : y.l[i]; });
-    Fr last;
-    canon<(W <= 5) ? 1 : 2>(last, r);
-    // w_i += b_i * y :  product < 1.854p, plus w_i < p  =>  < 2.854p < 4p
+    {
+        uint32_t r[9];
+        dot_mont<W>(
+            r, [&](int j, int k) { return j < t ? T::tab(base + 2 + t + j, k) : T::tab(base + 1, k); },
+            [&](int j, int i) { return j < t ? s[j].l[i] : y.l[i]; });
+        canon<(W <= 5) ? 1 : 2>(s[t], r);
+    }
+    // w_i += b_i * y :  product < 1.854p, plus w_i < p  =>  < 2.854p < 4p.  t trips on word 0, rotating
+    // the first t words (after t trips they are back in place).
+    Fr w[t];
 #pragma unroll
+    for (int i = 0; i < t; i++) w[i] = s[i];
+    HADES_NO_UNROLL
     for (int i = 0; i < t; i++) {
         uint32_t q[9];
+        const int bi = base + 2 + i;
         dot_mont<1>(
-            q, [&](int, int k) { return T::tab(base + 2 + i, k); }, [&](int, int limb) { return y.l[limb]; });
-        uint32_t sum[9];
-        uint32_t q8[8];
+            q, [&](int, int k) { return T::tab(bi, k); }, [&](int, int limb) { return y.l[limb]; });
+        uint32_t sum[9], q8[8], lo[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) q8[k] = q[k];
-        uint32_t lo[8];
-        uint32_t c = add8(lo, q8, s[i].l);
+        uint32_t c = add8(lo, q8, w[0].l);
 #pragma unroll
         for (int k = 0; k < 8; k++) sum[k] = lo[k];
         sum[8] = q[8] + c;
-        canon<1>(s[i], sum);
+        Fr res;
+        canon<1>(res, sum);
+        rotate_in<t>(w, res);
     }
-    s[t] = last;
+#pragma unroll
+    for (int i = 0; i < t; i++) s[i] = w[i];
 }
 
 template <int W, class T>

@@ -155,7 +155,7 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
     ctx->ops = width == 3 ? width_ops_3() : width == 5 ? width_ops_5() : width_ops_9();
-    ctx->variant = Variant{1, width == 3 ? 0 : width == 5 ? 1 : 2};  // spill-free register budgets
+    ctx->variant = Variant{1, width == 9 ? 2 : 0};  // spill-free register budgets
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
     std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
@@ -539,7 +539,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
 }
 
 int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
-    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 2) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
+    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 3) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     ctx->variant = Variant{algo, regs};
     return HADES_OK;
 }

@@ -136,22 +136,26 @@ sponge_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offs
 
 // ---- host-side launchers ---------------------------------------------------------------------------
 cudaError_t upload(const uint64_t* dense, const uint64_t* opt) {
-    cudaError_t e = cudaMemcpyToSymbol(c_dense, dense, sizeof(c_dense), 0, cudaMemcpyHostToDevice);
+    cudaError_t e = upload_modulus();
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_dense, dense, sizeof(c_dense), 0, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_opt, opt, sizeof(c_opt), 0, cudaMemcpyHostToDevice);
 }
 
-// regs: 0 -> minBlocks 4 (<=128 registers), 1 -> 3 (<=168), 2 -> 2 (<=255)
+// regs: 0 -> minBlocks 4 (<=128 registers), 1 -> 3 (<=168), 2 -> 2 (<=255), 3 -> 5 (<=96)
 #define HADES_DISPATCH(KERNEL, v, ...)                                                   \
     do {                                                                                 \
-        const int key_ = (v).algo * 3 + (v).regs;                                        \
+        const int key_ = (v).algo * 4 + (v).regs;                                        \
         switch (key_) {                                                                  \
             case 0: KERNEL<0, 4> __VA_ARGS__; break;                                     \
             case 1: KERNEL<0, 3> __VA_ARGS__; break;                                     \
             case 2: KERNEL<0, 2> __VA_ARGS__; break;                                     \
-            case 3: KERNEL<1, 4> __VA_ARGS__; break;                                     \
-            case 4: KERNEL<1, 3> __VA_ARGS__; break;                                     \
-            default: KERNEL<1, 2> __VA_ARGS__; break;                                    \
+            case 3: KERNEL<0, 5> __VA_ARGS__; break;                                     \
+            case 4: KERNEL<1, 4> __VA_ARGS__; break;                                     \
+            case 5: KERNEL<1, 3> __VA_ARGS__; break;                                     \
+            case 6: KERNEL<1, 2> __VA_ARGS__; break;                                     \
+            default: KERNEL<1, 5> __VA_ARGS__; break;                                    \
         }                                                                                \
     } while (0)
 
@@ -185,12 +189,14 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
 #endif
 
 #define HADES_ATTR(KERNEL, v, out)                                                       \
-    ((v).algo * 3 + (v).regs == 0   ? cudaFuncGetAttributes(out, KERNEL<0, 4>)           \
-     : (v).algo * 3 + (v).regs == 1 ? cudaFuncGetAttributes(out, KERNEL<0, 3>)           \
-     : (v).algo * 3 + (v).regs == 2 ? cudaFuncGetAttributes(out, KERNEL<0, 2>)           \
-     : (v).algo * 3 + (v).regs == 3 ? cudaFuncGetAttributes(out, KERNEL<1, 4>)           \
-     : (v).algo * 3 + (v).regs == 4 ? cudaFuncGetAttributes(out, KERNEL<1, 3>)           \
-                                    : cudaFuncGetAttributes(out, KERNEL<1, 2>))
+    ((v).algo * 4 + (v).regs == 0   ? cudaFuncGetAttributes(out, KERNEL<0, 4>)           \
+     : (v).algo * 4 + (v).regs == 1 ? cudaFuncGetAttributes(out, KERNEL<0, 3>)           \
+     : (v).algo * 4 + (v).regs == 2 ? cudaFuncGetAttributes(out, KERNEL<0, 2>)           \
+     : (v).algo * 4 + (v).regs == 3 ? cudaFuncGetAttributes(out, KERNEL<0, 5>)           \
+     : (v).algo * 4 + (v).regs == 4 ? cudaFuncGetAttributes(out, KERNEL<1, 4>)           \
+     : (v).algo * 4 + (v).regs == 5 ? cudaFuncGetAttributes(out, KERNEL<1, 3>)           \
+     : (v).algo * 4 + (v).regs == 6 ? cudaFuncGetAttributes(out, KERNEL<1, 2>)           \
+                                    : cudaFuncGetAttributes(out, KERNEL<1, 5>))
 
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
     if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);

@@ -11,7 +11,8 @@ namespace hades {
 // Kernel variants (runtime-selectable so that bench/tests can A/B them; all bit-identical):
 //   algo 0 = dense schedule (reference round structure, one lazily reduced dot product per MDS row)
 //   algo 1 = optimised schedule (sparse partial rounds, host_tables.hpp)
-//   regs 0 = __launch_bounds__(128, 4) (<=128 registers), 1 = (128, 3) (<=168), 2 = (128, 2) (<=255)
+//   regs 0 = __launch_bounds__(128, 4) (<=128 registers), 1 = (128, 3) (<=168), 2 = (128, 2) (<=255),
+//   3 = (128, 5) (<=96)
 struct Variant {
     int algo;
     int regs;
