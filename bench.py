@@ -54,6 +54,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", default=None, help="algo,regs kernel variant (default: library default)")
+    ap.add_argument("--workload", default="perm", choices=["perm", "merkle", "sponge", "sweep"],
+                    help="perm = BASELINE configs[1] (default, the contract line); merkle = configs[2]; "
+                         "sponge = configs[3]; sweep = configs[4]")
+    ap.add_argument("--log2-leaves", type=int, default=24)
+    ap.add_argument("--log2-msgs", type=int, default=22)
+    ap.add_argument("--verify", action="store_true", help="extras: compare against the CPU oracle (slow)")
     return ap.parse_args()
 
 
@@ -316,10 +322,211 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------ extra workloads
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return torch, dist, world, rank, local
+
+
+def run_merkle(args):
+    """BASELINE configs[2]: 4-ary Merkle root over 2^24 synthetic leaves, leaf ranges sharded over the
+    ranks, subtree roots all-gathered with NCCL, top levels finished on every rank."""
+    import numpy as np
+    torch, dist, world, rank, local = _dist_setup()
+    from hades252_b200 import CudaStrategy, sharding
+    strat = CudaStrategy([local])
+    n = 1 << args.log2_leaves
+    plan = sharding.merkle_plan(n, world)
+    lo, hi = sharding.shard_range(n, rank, world)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    leaves = torch.empty((hi - lo) * 4, dtype=torch.int64, device="cuda")
+    strat.gen_elems_device(leaves.data_ptr(), lo, hi - lo, SEED, sp)
+    scratch = torch.empty(((hi - lo) // 4 + (hi - lo) // 16 + 8) * 4, dtype=torch.int64, device="cuda")
+
+    def reduce_fn(nodes, levels):
+        n_nodes = nodes.numel() // 4
+        out = torch.empty((n_nodes >> (2 * levels)) * 4, dtype=torch.int64, device="cuda")
+        strat.merkle_reduce_device(nodes.data_ptr(), n_nodes, levels, scratch.data_ptr(), out.data_ptr(), sp)
+        return out
+
+    def all_gather_fn(roots):
+        bufs = torch.empty(world * roots.numel(), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(bufs, roots)
+        return bufs
+
+    def step():
+        return sharding.merkle_root_distributed(leaves, plan, reduce_fn, all_gather_fn)
+
+    for _ in range(args.warmup):
+        root = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = strat.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        root = step()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / args.steps
+    root_limbs = root.cpu().numpy().view(np.uint64)
+    if rank == 0:
+        n_perms = (n - 1) // 3
+        out = {"metric": "hades252_merkle_root_perms_per_sec", "value": n_perms / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "u32x8 (255-bit modular integer)", "data": "synthetic",
+               "config": {"workload": f"4-ary Merkle root over 2^{args.log2_leaves} leaves (BASELINE configs[2])",
+                          "plan": plan.__dict__, "collective": "ncclAllGather of subtree roots" if world > 1 else "none",
+                          "seed": hex(SEED)},
+               "root_mont_limbs": [hex(int(x)) for x in root_limbs], "gpu_launches": strat.launch_count - l0}
+        if args.verify:
+            from oracle import cpu_oracle
+            t = time.perf_counter()
+            want = cpu_oracle.merkle_root(cpu_oracle.gen_elems(0, n, SEED))
+            out["oracle_root_match"] = bool(np.array_equal(want, root_limbs))
+            out["oracle_seconds"] = time.perf_counter() - t
+        print(json.dumps(out))
+    strat.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sponge(args):
+    """BASELINE configs[3]: 2^22 messages of 1 + (splitmix64(seed2 + i) mod 32) elements, rate 4 / capacity 1."""
+    import numpy as np
+    torch, dist, world, rank, local = _dist_setup()
+    from hades252_b200 import CudaStrategy, sharding
+    strat = CudaStrategy([local])
+    n = 1 << args.log2_msgs
+    seed2 = SEED ^ 0x5A5A5A5A
+    idx = np.arange(n, dtype=np.uint64)
+    z = idx + np.uint64(seed2) + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+    lens = (z % np.uint64(32)) + np.uint64(1)
+    offsets = np.concatenate([[np.uint64(0)], np.cumsum(lens, dtype=np.uint64)])
+    m0, m1 = sharding.sponge_partition(offsets, world)[rank]
+    e0_, e1_ = int(offsets[m0]), int(offsets[m1])
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    elems = torch.empty(max(e1_ - e0_, 1) * 4, dtype=torch.int64, device="cuda")
+    strat.gen_elems_device(elems.data_ptr(), e0_, e1_ - e0_, SEED, sp)
+    d_off = torch.from_numpy((offsets[m0:m1 + 1] - offsets[m0]).view(np.int64)).cuda()
+    out_d = torch.empty((m1 - m0) * 4, dtype=torch.int64, device="cuda")
+    for _ in range(args.warmup):
+        strat.sponge_batch_device(elems.data_ptr(), d_off.data_ptr(), m1 - m0, out_d.data_ptr(), sp)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = strat.launch_count
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.steps):
+        strat.sponge_batch_device(elems.data_ptr(), d_off.data_ptr(), m1 - m0, out_d.data_ptr(), sp)
+    b.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / args.steps
+    if rank == 0:
+        perms = int(sharding.sponge_perm_counts(offsets).sum())
+        res = {"metric": "hades252_sponge_perms_per_sec", "value": perms / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "u32x8 (255-bit modular integer)", "data": "synthetic",
+               "config": {"workload": f"sponge of 2^{args.log2_msgs} variable-length messages (BASELINE configs[3])",
+                          "messages": n, "elements": int(offsets[-1]), "perms": perms, "messages_per_s": n / (ms * 1e-3),
+                          "length_bucketing": "device radix sort by perm count", "seed": hex(SEED)},
+               "gpu_launches": strat.launch_count - l0}
+        if args.verify:
+            from oracle import cpu_oracle
+            k = min(m1 - m0, 1 << 16)
+            sub_off = (offsets[m0:m0 + k + 1] - offsets[m0]).astype(np.uint64)
+            want = cpu_oracle.sponge_batch(cpu_oracle.gen_elems(e0_, int(sub_off[-1]), SEED), sub_off)
+            got = out_d.cpu().numpy().view(np.uint64).reshape(-1, 4)[:k]
+            res["oracle_match_first_2p16"] = bool(np.array_equal(want, got))
+        print(json.dumps(res))
+    strat.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sweep(args):
+    """BASELINE configs[4]: perms/s for widths 3, 5, 9 over batch sizes 2^16 .. 2^log2_states per GPU.
+    Sizes above 2^26 states are processed in 2^26-state chunks (regenerated per chunk) so that the
+    job fits one GPU's HBM."""
+    import numpy as np
+    torch, dist, world, rank, local = _dist_setup()
+    from hades252_b200 import CudaStrategy
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    rows = []
+    for w in (3, 5, 9):
+        strat = CudaStrategy([local], width=w)
+        for l2 in range(16, args.log2_states + 1, 2):
+            n = 1 << l2
+            chunk = min(n, 1 << 26 if w < 9 else 1 << 25)
+            buf = torch.empty(chunk * w * 4, dtype=torch.int64, device="cuda")
+            strat.gen_elems_device(buf.data_ptr(), rank * n * w, chunk * w, SEED, sp)
+            strat.perm_batch_device(buf.data_ptr(), chunk, sp)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(1, min(5, (1 << 24) // n))
+            a.record(stream)
+            for _ in range(reps):
+                for off in range(0, n, chunk):
+                    if n > chunk:
+                        strat.gen_elems_device(buf.data_ptr(), (rank * n + off) * w, chunk * w, SEED, sp)
+                    strat.perm_batch_device(buf.data_ptr(), chunk, sp)
+            b.record(stream)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            rows.append({"width": w, "log2_states_per_gpu": l2, "n_gpus": world, "ms": float(ms.item()),
+                         "perms_per_s": world * n / (float(ms.item()) * 1e-3)})
+            del buf
+        strat.close()
+    if rank == 0:
+        print(json.dumps({"metric": "hades252_sweep_perms_per_sec", "unit": UNIT, "n_gpus": world, "data": "synthetic",
+                          "config": {"workload": "throughput sweep (BASELINE configs[4])"}, "rows": rows}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "merkle":
+        run_merkle(args)
+    elif args.workload == "sponge":
+        run_sponge(args)
+    elif args.workload == "sweep":
+        run_sweep(args)
     else:
         run_ours(args)
 

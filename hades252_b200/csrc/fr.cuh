@@ -16,7 +16,8 @@
 //  * word-serial Montgomery reduction interleaved with the products (CIOS), generalised to an
 //    N-term dot product  sum_j c_j*v_j  that is reduced ONCE (lazy reduction of an MDS row);
 //  * special modulus: p[0] = 1 and -p^{-1} mod 2^32 = 0xffffffff, so the Montgomery quotient is
-//    m = -t0 (no multiply) and m*p[0] needs no product: 7 products per reduction step.
+//    m = -t0 (no multiply); m*p[0] and m*p[1] (p[1] = 2^32 - 1) need no product: 6 products per
+//    reduction step, the rest is two adds on the ALU pipe.
 //
 // The same source compiles with g++ -DHADES_HOST_EMUL (tests/host_emul): the PTX chains are then
 // replaced by portable C++ of identical semantics, so the limb-level algorithm is checked against
@@ -169,6 +170,37 @@ HADES_DEV void redc_even(uint32_t (&acc)[9], uint32_t m) {
 #endif
 }
 
+// Montgomery step on the accumulator that starts one limb higher ("odd": limb k = position k+1).
+// The two low limbs of p are 2^64 - 2^32 + 1, so with t0 = even[0], m = -t0, nz = (t0 != 0):
+//   t0 + m*(p0 + p1*2^32) = nz*2^32 + t0*2^32 + (m - nz)*2^64
+// i.e. m*p[1] needs no product: position 1 gets +t0 (the +nz is the carry of even[0] + m, already
+// added by redc_even) and position 2 gets +(m - nz).  3 products (p3, p5, p7) instead of 4.
+HADES_DEV void redc_odd(uint32_t (&acc)[9], uint32_t t0, uint32_t m) {
+    // m - nz without a branch: m == 0 iff t0 == 0
+    uint32_t mm = (m > 1u ? m : 1u) - 1u;
+#if !HADES_EMUL
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "madc.lo.cc.u32 %2, %11, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %14, %6;\n\t"
+        "madc.hi.cc.u32 %7, %11, %14, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(t0), "r"(mm), "r"(m), "r"(modp(3)), "r"(modp(5)), "r"(modp(7)));
+#else
+    uint64_t s = (uint64_t)acc[0] + t0;
+    acc[0] = (uint32_t)s;
+    s = (uint64_t)acc[1] + mm + (s >> 32);
+    acc[1] = (uint32_t)s;
+    const uint32_t a[4] = {0, p_limb(3), p_limb(5), p_limb(7)};
+    emul::top(acc[8], emul::chain(acc, a, 1, m, s >> 32));
+#endif
+}
+
 // r[0..8] = even + (odd << 32) + x   (x at limb 0); the discarded limb above r[8] must be zero.
 HADES_DEV void merge_even_odd(uint32_t (&r)[9], const uint32_t (&e)[9], const uint32_t (&o)[9], uint32_t x) {
 #if !HADES_EMUL
@@ -263,6 +295,35 @@ HADES_DEV uint32_t add8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t
     return carry;
 }
 
+// r = a + b + cin (cin = 0/1) over 8 limbs, returns the carry-out limb (0/1).
+HADES_DEV uint32_t add8_cin(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t cin) {
+    uint32_t carry;
+#if !HADES_EMUL
+    asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"  // carry flag := cin
+        "addc.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=&r"(carry)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+#else
+    uint64_t s = (uint64_t)cin << 32;
+    for (int k = 0; k < 8; k++) {
+        s = (uint64_t)a[k] + b[k] + (s >> 32);
+        r[k] = (uint32_t)s;
+    }
+    carry = (uint32_t)(s >> 32);
+#endif
+    return carry;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Reductions to the canonical range
 // ------------------------------------------------------------------------------------------------
@@ -324,8 +385,9 @@ HADES_DEV void dot_step(uint32_t (&E)[9], uint32_t (&O)[9], uint32_t x, int i, V
     // Written as (E0 ^ p[1]) + p[0] = ~E0 + 1 with the two limbs read from constant memory: if ptxas
     // can prove m == -E0 it rewrites every m*p[k] product into IMAD.X + IMAD.HI.U32.X pairs
     // (7.1 pipe cycles instead of 4.05).
-    uint32_t m = (E[0] ^ modp(1)) + modp(0);
-    cmad4(O, modp(1), modp(3), modp(5), modp(7), m);
+    uint32_t t0 = E[0];
+    uint32_t m = (t0 ^ modp(1)) + modp(0);
+    redc_odd(O, t0, m);
     redc_even(E, m);
 }
 
@@ -356,6 +418,246 @@ HADES_DEV void dot_mont(uint32_t (&r)[9], Vec vec, Sca sca) {
     merge_even_odd(r, A, B, x);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dedicated Montgomery squaring: 28 off-diagonal + 8 diagonal + 48 reduction = 84 products (a general
+// product costs 64 + 48 = 112).
+// ------------------------------------------------------------------------------------------------
+// Short chains for the triangle a_i*a_j (i<j): L links on consecutive 64-bit columns, carry-out added
+// to the limb right above (`land`).  Rows are processed in ascending i, which guarantees that a landing
+// limb only ever holds a few carries when it is hit (never a product limb), so no ripple is possible.
+HADES_DEV void cmad1(uint32_t& l0, uint32_t& h0, uint32_t& land, uint32_t a0, uint32_t b) {
+#if !HADES_EMUL
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(l0), "+r"(h0), "+r"(land)
+        : "r"(a0), "r"(b));
+#else
+    uint32_t acc[2] = {l0, h0};
+    const uint32_t a[4] = {0, 0, 0, a0};
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, acc[0], acc[1]};
+    uint64_t c = emul::chain(w, a, 3, b, 0);
+    l0 = w[6]; h0 = w[7];
+    emul::top(land, c);
+#endif
+}
+HADES_DEV void cmad2(uint32_t& l0, uint32_t& h0, uint32_t& l1, uint32_t& h1, uint32_t& land, uint32_t a0, uint32_t a1,
+                     uint32_t b) {
+#if !HADES_EMUL
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(l0), "+r"(h0), "+r"(l1), "+r"(h1), "+r"(land)
+        : "r"(a0), "r"(a1), "r"(b));
+#else
+    const uint32_t a[4] = {0, 0, a0, a1};
+    uint32_t w[8] = {0, 0, 0, 0, l0, h0, l1, h1};
+    uint64_t c = emul::chain(w, a, 2, b, 0);
+    l0 = w[4]; h0 = w[5]; l1 = w[6]; h1 = w[7];
+    emul::top(land, c);
+#endif
+}
+HADES_DEV void cmad3(uint32_t& l0, uint32_t& h0, uint32_t& l1, uint32_t& h1, uint32_t& l2, uint32_t& h2, uint32_t& land,
+                     uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+#if !HADES_EMUL
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(l0), "+r"(h0), "+r"(l1), "+r"(h1), "+r"(l2), "+r"(h2), "+r"(land)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#else
+    const uint32_t a[4] = {0, a0, a1, a2};
+    uint32_t w[8] = {0, 0, l0, h0, l1, h1, l2, h2};
+    uint64_t c = emul::chain(w, a, 1, b, 0);
+    l0 = w[2]; h0 = w[3]; l1 = w[4]; h1 = w[5]; l2 = w[6]; h2 = w[7];
+    emul::top(land, c);
+#endif
+}
+HADES_DEV void cmad4r(uint32_t& l0, uint32_t& h0, uint32_t& l1, uint32_t& h1, uint32_t& l2, uint32_t& h2, uint32_t& l3,
+                      uint32_t& h3, uint32_t& land, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    uint32_t acc[9] = {l0, h0, l1, h1, l2, h2, l3, h3, land};
+    cmad4(acc, a0, a1, a2, a3, b);
+    l0 = acc[0]; h0 = acc[1]; l1 = acc[2]; h1 = acc[3]; l2 = acc[4]; h2 = acc[5]; l3 = acc[6]; h3 = acc[7]; land = acc[8];
+}
+
+// t[0..15] = 2*t + sum_i a_i^2 * 2^(64 i)   (t < 2^511 on entry; the result a^2-part fits 512 bits)
+HADES_DEV void double_add_diag(uint32_t (&t)[16], const uint32_t (&a)[8]) {
+#if !HADES_EMUL
+    uint32_t d[16];
+    d[0] = t[0] << 1;
+#pragma unroll
+    for (int k = 1; k < 16; k++) d[k] = __funnelshift_l(t[k - 1], t[k], 1);
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]), "+r"(d[8]),
+          "+r"(d[9]), "+r"(d[10]), "+r"(d[11]), "+r"(d[12]), "+r"(d[13]), "+r"(d[14]), "+r"(d[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = d[k];
+#else
+    HADES_ASSERT((t[15] >> 31) == 0);
+    uint32_t d[16];
+    d[0] = t[0] << 1;
+    for (int k = 1; k < 16; k++) d[k] = (t[k] << 1) | (t[k - 1] >> 31);
+    uint64_t carry = 0;
+    for (int i = 0; i < 8; i++) {
+        unsigned __int128 v = (unsigned __int128)a[i] * a[i] + (((uint64_t)d[2 * i + 1] << 32) | d[2 * i]) + carry;
+        d[2 * i] = (uint32_t)v;
+        d[2 * i + 1] = (uint32_t)(v >> 32);
+        carry = (uint64_t)(v >> 64);
+    }
+    HADES_ASSERT(carry == 0);
+    for (int k = 0; k < 16; k++) t[k] = d[k];
+#endif
+}
+
+// e0 += x, returns the carry (0/1)
+HADES_DEV uint32_t add_carry_out(uint32_t& e0, uint32_t x) {
+    uint32_t c;
+#if !HADES_EMUL
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(e0), "=r"(c) : "r"(x));
+#else
+    uint64_t s = (uint64_t)e0 + x;
+    e0 = (uint32_t)s;
+    c = (uint32_t)(s >> 32);
+#endif
+    return c;
+}
+
+// redc_even with an extra carry `cx` (0/1) entering limb 1
+HADES_DEV void redc_even_c(uint32_t (&acc)[9], uint32_t m, uint32_t cx) {
+#if !HADES_EMUL
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %13;\n\t"
+        "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, %12, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, %12, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(m), "r"(modp(2)), "r"(modp(4)), "r"(modp(6)), "r"(cx));
+#else
+    uint64_t s = (uint64_t)acc[0] + m;
+    acc[0] = (uint32_t)s;
+    HADES_ASSERT(acc[0] == 0);
+    s = (uint64_t)acc[1] + cx + (s >> 32);
+    acc[1] = (uint32_t)s;
+    const uint32_t a[4] = {0, p_limb(2), p_limb(4), p_limb(6)};
+    emul::top(acc[8], emul::chain(acc, a, 1, m, s >> 32));
+#endif
+}
+
+// r = t / 2^256 mod p (9 limbs, < t/2^256 + p) for a merged 512-bit t: the reduce-only version of
+// dot_mont -- same even/odd bookkeeping, the upper limbs of t are injected one per shift.
+HADES_DEV void redc16(uint32_t (&r)[9], const uint32_t (&t)[16]) {
+    uint32_t A[9], B[9];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { A[k] = t[k]; B[k] = 0; }
+    A[8] = 0; B[8] = 0;
+    B[7] = t[8];  // odd accumulator limb k sits at position k + 1
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        {  // step i: E = A, O = B
+            uint32_t cx = (i == 0) ? 0u : add_carry_out(A[0], x);
+            uint32_t t0 = A[0];
+            uint32_t m = (t0 ^ modp(1)) + modp(0);
+            redc_odd(B, t0, m);
+            redc_even_c(A, m, cx);
+            x = A[1];
+#pragma unroll
+            for (int k = 0; k < 7; k++) A[k] = A[k + 2];
+            A[7] = t[i + 9];
+            A[8] = 0;
+        }
+        {  // step i+1: E = B, O = A
+            uint32_t cx = add_carry_out(B[0], x);
+            uint32_t t0 = B[0];
+            uint32_t m = (t0 ^ modp(1)) + modp(0);
+            redc_odd(A, t0, m);
+            redc_even_c(B, m, cx);
+            x = B[1];
+#pragma unroll
+            for (int k = 0; k < 7; k++) B[k] = B[k + 2];
+            B[7] = (i + 10 < 16) ? t[i + 10] : 0u;
+            B[8] = 0;
+        }
+    }
+    merge_even_odd(r, A, B, x);
+}
+
+// r = a^2 / 2^256 mod p, 9 limbs, value < a^2/2^256 + p
+HADES_DEV void sqr_mont(uint32_t (&r)[9], const uint32_t (&a)[8]) {
+    uint32_t E[17], O[16];  // E[k] = position k, O[k] = position k + 1
+#pragma unroll
+    for (int k = 0; k < 17; k++) E[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) O[k] = 0;
+    // row 0: a0 * a[1..7]
+    cmad4r(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], O[8], a[1], a[3], a[5], a[7], a[0]);
+    cmad3(E[2], E[3], E[4], E[5], E[6], E[7], E[8], a[2], a[4], a[6], a[0]);
+    // row 1: a1 * a[2..7]
+    cmad3(E[4], E[5], E[6], E[7], E[8], E[9], E[10], a[3], a[5], a[7], a[1]);
+    cmad3(O[2], O[3], O[4], O[5], O[6], O[7], O[8], a[2], a[4], a[6], a[1]);
+    // row 2: a2 * a[3..7]
+    cmad3(O[4], O[5], O[6], O[7], O[8], O[9], O[10], a[3], a[5], a[7], a[2]);
+    cmad2(E[6], E[7], E[8], E[9], E[10], a[4], a[6], a[2]);
+    // row 3: a3 * a[4..7]
+    cmad2(E[8], E[9], E[10], E[11], E[12], a[5], a[7], a[3]);
+    cmad2(O[6], O[7], O[8], O[9], O[10], a[4], a[6], a[3]);
+    // row 4: a4 * a[5..7]
+    cmad2(O[8], O[9], O[10], O[11], O[12], a[5], a[7], a[4]);
+    cmad1(E[10], E[11], E[12], a[6], a[4]);
+    // row 5: a5 * a[6..7]
+    cmad1(E[12], E[13], E[14], a[7], a[5]);
+    cmad1(O[10], O[11], O[12], a[6], a[5]);
+    // row 6: a6 * a7
+    cmad1(O[12], O[13], O[14], a[7], a[6]);
+    // merge: t = E + (O << 32), 16 limbs (the triangle is < 2^511)
+    uint32_t t[16];
+    {
+        uint32_t lo[8], hi[8], e_lo[8], e_hi[8], o_lo[8], o_hi[8];
+        e_lo[0] = E[0];
+        o_lo[0] = 0;
+#pragma unroll
+        for (int k = 1; k < 8; k++) { e_lo[k] = E[k]; o_lo[k] = O[k - 1]; }
+        e_lo[0] = E[0];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { e_hi[k] = E[8 + k]; o_hi[k] = O[7 + k]; }
+        uint32_t c = add8(lo, e_lo, o_lo);
+        uint32_t c2 = add8_cin(hi, e_hi, o_hi, c);
+        HADES_ASSERT(c2 == 0 && E[16] == 0 && O[15] == 0);  // the triangle is < 2^511
+        (void)c2;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { t[k] = lo[k]; t[8 + k] = hi[k]; }
+    }
+    double_add_diag(t, a);
+    redc16(r, t);
+}
+
 // out = a*b/R mod p, canonical.  a,b canonical (or any a,b with a*b < p*R).
 HADES_DEV void fr_mul(Fr& out, const Fr& a, const Fr& b) {
     uint32_t r[9];
@@ -375,10 +677,18 @@ HADES_DEV void fr_mul_lazy(Fr& out, const Fr& a, const Fr& b) {
 // x -> x^5 (scalar.rs:32-34 `value.square().square() * value`), canonical in, canonical out.
 // Bounds with x < p (p/R = 0.4528): x^2 < 1.453p, x^4 < 1.956p, x^5 < 1.886p -- all below 2^256,
 // so only the last product needs the conditional subtraction.
+HADES_DEV void fr_sqr_lazy(Fr& out, const Fr& a) {
+    uint32_t r[9];
+    sqr_mont(r, a.l);
+    HADES_ASSERT(r[8] == 0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out.l[k] = r[k];
+}
+
 HADES_DEV void fr_sbox(Fr& x) {
     Fr x2, x4;
-    fr_mul_lazy(x2, x, x);
-    fr_mul_lazy(x4, x2, x2);
+    fr_sqr_lazy(x2, x);
+    fr_sqr_lazy(x4, x2);
     fr_mul(x, x4, x);
 }
 

@@ -172,8 +172,8 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
         fr_add(s[t], s[t], e);
     }
     Fr y, x2, x4;
-    fr_mul_lazy(x2, s[t], s[t]);
-    fr_mul_lazy(x4, x2, x2);
+    fr_sqr_lazy(x2, s[t]);
+    fr_sqr_lazy(x4, x2);
     fr_mul_lazy(y, x4, s[t]);
     // new last word = sum_{j<t} chat_j * w_j + d * y  (uses the OLD w_j)
     // bound: (t + 1.886) p^2  =>  < p (1 + 0.4528 (t + 1.886)): W=5 -> 3.67p, W=9 -> 5.48p
@@ -210,7 +210,13 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
     for (int i = 0; i < t; i++) s[i] = w[i];
 }
 
-template <int W, class T>
+struct NoSync {
+    static HADES_DEV void sync() {}
+};
+
+// `Sync::sync()` is called once per round; kernels with uniform control flow pass a block barrier so
+// that the warps of a block stay in lockstep and share instruction-cache lines.
+template <int W, class T, class Sync = NoSync>
 HADES_DEV void hades_perm_opt(Fr (&s)[W]) {
     typedef OptLayout<W> L;
     constexpr int kHalf = kFullRounds / 2;
@@ -219,12 +225,16 @@ HADES_DEV void hades_perm_opt(Fr (&s)[W]) {
 #endif
     for (int f = 0; f < kFullRounds; f++) {
         full_round_opt<W, T>(s, L::kArk + f * W, (f == kHalf - 1) ? L::kPre : L::kMds);
+        Sync::sync();
         if (f == kHalf - 1) {
             add_table_vector<W, T>(s, L::kC4);
 #if !HADES_EMUL
 #pragma unroll 1
 #endif
-            for (int q = 0; q < kPartialRounds; q++) partial_round_opt<W, T>(s, L::kSparse + q * L::kSparseStride);
+            for (int q = 0; q < kPartialRounds; q++) {
+                partial_round_opt<W, T>(s, L::kSparse + q * L::kSparseStride);
+                Sync::sync();
+            }
         }
     }
 }

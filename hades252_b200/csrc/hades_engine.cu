@@ -4,6 +4,8 @@
 // or fails with a status code.
 #include <cuda_runtime.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -155,7 +157,7 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
     ctx->ops = width == 3 ? width_ops_3() : width == 5 ? width_ops_5() : width_ops_9();
-    ctx->variant = Variant{1, width == 9 ? 2 : 0};  // spill-free register budgets
+    ctx->variant = Variant{1, width == 9 ? 2 : 4};  // W=9 needs 238 registers; others: lockstep 256-thread blocks
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
     std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
@@ -368,10 +370,31 @@ int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elem
     if (n_msgs == 0) return HADES_OK;
     if (!d_offsets || !d_out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     if (((uintptr_t)d_elems | (uintptr_t)d_out) & 15) return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    if (n_msgs > 0x7fffffffULL) return fail(ctx, HADES_ERR_INVALID_ARG, "too many messages for one call");
+    cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    // Length bucketing: sort message indices by permutation count so that the 32 messages of a warp
+    // need the same number of perms (a strictly sequential chain per message).
+    uint32_t *keys = nullptr, *keys_out = nullptr, *idx = nullptr, *order = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int n = (int)n_msgs;
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
+    CUDA_TRY(ctx, cudaMallocAsync(&keys, n_msgs * 4, st));
+    CUDA_TRY(ctx, cudaMallocAsync(&keys_out, n_msgs * 4, st));
+    CUDA_TRY(ctx, cudaMallocAsync(&idx, n_msgs * 4, st));
+    CUDA_TRY(ctx, cudaMallocAsync(&order, n_msgs * 4, st));
+    CUDA_TRY(ctx, cudaMallocAsync(&tmp, tmp_bytes, st));
+    sponge_keys_kernel<<<(unsigned)std::min<size_t>((n_msgs + 255) / 256, 148 * 16), 256, 0, st>>>(d_offsets, keys, idx, n_msgs);
     ctx->launches++;
-    CUDA_TRY(ctx, ctx->ops->launch_sponge(ctx->variant, d_elems, d_offsets, nullptr, d_out, n_msgs, (cudaStream_t)stream));
-    return HADES_OK;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
+    ctx->launches++;
+    int rc = HADES_OK;
+    cudaError_t e = ctx->ops->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, st);
+    if (e != cudaSuccess) rc = fail(ctx, HADES_ERR_CUDA, "sponge launch failed: %s", cudaGetErrorString(e));
+    cudaFreeAsync(keys, st); cudaFreeAsync(keys_out, st); cudaFreeAsync(idx, st); cudaFreeAsync(order, st); cudaFreeAsync(tmp, st);
+    return rc;
 }
 
 int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs, uint64_t* out) {
@@ -379,66 +402,51 @@ int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* of
     if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "sponge needs a width-5 context");
     if (n_msgs == 0) return HADES_OK;
     if (!offsets || !out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
-    const size_t n_elems = offsets[n_msgs] - offsets[0];
-    if (n_elems && !elems) return fail(ctx, HADES_ERR_INVALID_ARG, "null elems pointer");
     for (size_t m = 0; m < n_msgs; m++)
         if (offsets[m + 1] < offsets[m]) return fail(ctx, HADES_ERR_INVALID_ARG, "offsets must be non-decreasing");
-    if (n_msgs > 0xffffffffULL) return fail(ctx, HADES_ERR_INVALID_ARG, "too many messages for one call");
-    // order messages by block count so that the 32 messages of a warp need the same number of perms
-    std::vector<uint32_t> order(n_msgs);
-    {
-        size_t max_blocks = 0;
-        for (size_t m = 0; m < n_msgs; m++) max_blocks = std::max<size_t>(max_blocks, (offsets[m + 1] - offsets[m]) / 4 + 1);
-        std::vector<size_t> start(max_blocks + 2, 0);
-        for (size_t m = 0; m < n_msgs; m++) start[(offsets[m + 1] - offsets[m]) / 4 + 2]++;
-        for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
-        for (size_t m = 0; m < n_msgs; m++) order[start[(offsets[m + 1] - offsets[m]) / 4 + 1]++] = (uint32_t)m;
-    }
-    // shard the ORDERED message list over the devices (interleaved so every device sees every length)
+    if (offsets[n_msgs] > offsets[0] && !elems) return fail(ctx, HADES_ERR_INVALID_ARG, "null elems pointer");
+    // contiguous message ranges per device, balanced by permutation count (floor(len/4) + 1 each)
     const size_t G = std::min<size_t>(ctx->devs.size(), std::max<size_t>(1, n_msgs / 4096));
-    struct Bufs { uint64_t *elems = nullptr, *offsets = nullptr, *out = nullptr; uint32_t* order = nullptr; };
+    std::vector<size_t> bound(G + 1, n_msgs);
+    bound[0] = 0;
+    if (G > 1) {
+        uint64_t total = 0;
+        for (size_t m = 0; m < n_msgs; m++) total += (offsets[m + 1] - offsets[m]) / 4 + 1;
+        uint64_t acc = 0;
+        size_t g = 1;
+        for (size_t m = 0; m < n_msgs && g < G; m++) {
+            acc += (offsets[m + 1] - offsets[m]) / 4 + 1;
+            while (g < G && acc >= total * g / G) bound[g++] = m + 1;
+        }
+    }
+    struct Bufs { uint64_t *elems = nullptr, *offsets = nullptr, *out = nullptr; };
     std::vector<Bufs> bufs(G);
-    std::vector<std::vector<uint32_t>> dev_order(G);
-    for (size_t t = 0; t < n_msgs; t++) dev_order[(t / 32) % G].push_back(order[t]);
     int rc = HADES_OK;
     for (size_t g = 0; g < G && rc == HADES_OK; g++) {
         auto step = [&]() -> int {
             DeviceState& d = ctx->devs[g];
-            size_t cnt = dev_order[g].size();
+            const size_t m0 = bound[g], cnt = bound[g + 1] - bound[g];
             if (!cnt) return HADES_OK;
+            const uint64_t e0 = offsets[m0], ne = offsets[m0 + cnt] - e0;
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            // every device receives the whole CSR arrays (elements are read-only and shared);
-            // only `order` and the written digests are per device
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].elems, std::max<size_t>(n_elems, 1) * 32));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].offsets, (n_msgs + 1) * 8));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].out, n_msgs * 32));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].order, cnt * 4));
-            if (n_elems)
-                CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].elems, elems + offsets[0] * 4, n_elems * 32, cudaMemcpyHostToDevice, d.streams[0]));
-            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].offsets, offsets, (n_msgs + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
-            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].order, dev_order[g].data(), cnt * 4, cudaMemcpyHostToDevice, d.streams[0]));
-            // offsets are absolute: bias the element base pointer by offsets[0]
-            const uint64_t* ebase = bufs[g].elems - offsets[0] * 4;
-            ctx->launches++;
-            CUDA_TRY(ctx, ctx->ops->launch_sponge(ctx->variant, ebase, bufs[g].offsets, bufs[g].order, bufs[g].out, cnt, d.streams[0]));
-            if (G == 1) CUDA_TRY(ctx, cudaMemcpyAsync(out, bufs[g].out, n_msgs * 32, cudaMemcpyDeviceToHost, d.streams[0]));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].elems, std::max<uint64_t>(ne, 1) * 32));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].offsets, (cnt + 1) * 8));
+            CUDA_TRY(ctx, cudaMalloc(&bufs[g].out, cnt * 32));
+            if (ne) CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].elems, elems + e0 * 4, ne * 32, cudaMemcpyHostToDevice, d.streams[0]));
+            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].offsets, offsets + m0, (cnt + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
+            // offsets stay absolute: bias the element base pointer by the range's first offset
+            int r = hades_sponge_batch_dev(ctx, (int)g, bufs[g].elems - e0 * 4, bufs[g].offsets, cnt, bufs[g].out, d.streams[0]);
+            if (r) return r;
+            CUDA_TRY(ctx, cudaMemcpyAsync(out + m0 * 4, bufs[g].out, cnt * 32, cudaMemcpyDeviceToHost, d.streams[0]));
             return HADES_OK;
         };
         rc = step();
     }
-    std::vector<uint64_t> tmp;
     for (size_t g = 0; g < G; g++) {
         cudaSetDevice(ctx->devs[g].ordinal);
         cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[0]);
         if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "sponge pass failed: %s", cudaGetErrorString(e));
-        if (rc == HADES_OK && G > 1 && !dev_order[g].empty()) {
-            // digests were scattered by message index into a full-size buffer: pick this device's
-            tmp.resize(n_msgs * 4);
-            e = cudaMemcpy(tmp.data(), bufs[g].out, n_msgs * 32, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) rc = fail(ctx, HADES_ERR_CUDA, "sponge D2H failed: %s", cudaGetErrorString(e));
-            else for (uint32_t m : dev_order[g]) memcpy(out + (size_t)m * 4, tmp.data() + (size_t)m * 4, 32);
-        }
-        cudaFree(bufs[g].elems); cudaFree(bufs[g].offsets); cudaFree(bufs[g].out); cudaFree(bufs[g].order);
+        cudaFree(bufs[g].elems); cudaFree(bufs[g].offsets); cudaFree(bufs[g].out);
     }
     return rc;
 }
@@ -539,7 +547,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
 }
 
 int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
-    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 3) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
+    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 5) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     ctx->variant = Variant{algo, regs};
     return HADES_OK;
 }

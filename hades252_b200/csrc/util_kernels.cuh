@@ -46,6 +46,15 @@ __global__ void digest_kernel(const uint64_t* __restrict__ limbs, uint64_t first
     }
 }
 
+// sponge length bucketing: key = permutations needed by message m = floor(len / 4) + 1, value = m
+__global__ void sponge_keys_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ keys,
+                                   uint32_t* __restrict__ idx, size_t n_msgs) {
+    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n_msgs; m += (size_t)gridDim.x * blockDim.x) {
+        keys[m] = (uint32_t)((offsets[m + 1] - offsets[m]) / 4 + 1);
+        idx[m] = (uint32_t)m;
+    }
+}
+
 // ---- integer-multiply roofline microbenchmark --------------------------------------------------------
 // 8 independent accumulators per thread, 8 unrolled steps per loop iteration; multiplicands come from
 // the neighbouring accumulator so nothing is loop-invariant or warp-uniform (ptxas otherwise hoists the

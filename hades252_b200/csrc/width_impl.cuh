@@ -63,6 +63,26 @@ __global__ void __launch_bounds__(kPermThreads, MINB) perm_batch_kernel(uint4* _
     for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
 }
 
+// Lockstep variant: BLOCK threads per block, one barrier per round; out-of-range threads compute on the
+// last state and skip the store so that every thread reaches every barrier.
+struct BlockSync {
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) perm_batch_lockstep_kernel(uint4* __restrict__ states, size_t n) {
+    size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = i < n;
+    uint4* p = states + (live ? i : n - 1) * (2 * W);
+    Fr s[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) fr_load(s[j], p + 2 * j);
+    hades_perm_opt<W, OptTab, BlockSync>(s);
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
+    }
+}
+
 #if HADES_W == 5
 // Montgomery forms of the two small constants the compositions need (checked in tests).
 __device__ __forceinline__ void fr_set_one(Fr& x) {  // 1 * R mod p
@@ -161,8 +181,14 @@ cudaError_t upload(const uint64_t* dense, const uint64_t* opt) {
 
 cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
+    if (v.algo == 1 && v.regs >= 4) {  // lockstep launches: regs 4 -> 256 threads per block, 5 -> 512
+        if (v.regs == 4) perm_batch_lockstep_kernel<256, 2><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(d_states), n);
+        else perm_batch_lockstep_kernel<512, 1><<<(unsigned)((n + 511) / 512), 512, 0, s>>>(reinterpret_cast<uint4*>(d_states), n);
+        return cudaGetLastError();
+    }
     size_t blocks = (n + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
+    if (v.regs >= 4) v.regs = 0;  // dense schedule has no lockstep build
     HADES_DISPATCH(perm_batch_kernel, v, <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<uint4*>(d_states), n));
     return cudaGetLastError();
 }
@@ -170,6 +196,7 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
 #if HADES_W == 5
 cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s) {
     if (n_out == 0) return cudaSuccess;
+    if (v.regs >= 4) v.regs = 0;
     size_t blocks = (n_out + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     HADES_DISPATCH(merkle_level_kernel, v,
@@ -179,6 +206,7 @@ cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out
 cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
                           uint64_t* d_out, size_t n_threads, cudaStream_t s) {
     if (n_threads == 0) return cudaSuccess;
+    if (v.regs >= 4) v.regs = 0;
     size_t blocks = (n_threads + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     HADES_DISPATCH(sponge_kernel, v,
@@ -199,6 +227,9 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
                                     : cudaFuncGetAttributes(out, KERNEL<1, 5>))
 
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 5) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<512, 1>);
+    if (v.regs >= 4) v.regs = 0;  // merkle / sponge / dense: plain 128-thread launches
     if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);
 #if HADES_W == 5
     if (!strcmp(kernel, "merkle")) return HADES_ATTR(merkle_level_kernel, v, out);

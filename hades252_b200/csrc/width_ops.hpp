@@ -12,7 +12,8 @@ namespace hades {
 //   algo 0 = dense schedule (reference round structure, one lazily reduced dot product per MDS row)
 //   algo 1 = optimised schedule (sparse partial rounds, host_tables.hpp)
 //   regs 0 = __launch_bounds__(128, 4) (<=128 registers), 1 = (128, 3) (<=168), 2 = (128, 2) (<=255),
-//   3 = (128, 5) (<=96)
+//   3 = (128, 5) (<=96); 4 / 5 = lockstep blocks of 256 / 512 threads with one barrier per round
+//   (optimised perm kernel only; keeps the warps of a block on the same instruction-cache lines)
 struct Variant {
     int algo;
     int regs;

@@ -102,6 +102,21 @@ int main(int argc, char** argv) {
         uint64_t x2[4], x4[4]; oracle_fr_mul(a, a, x2); oracle_fr_mul(x2, x2, x4); oracle_fr_mul(x4, a, want);
         if (memcmp(got, want, 32)) { printf("sbox mismatch %d\n", it); return 1; }
     }
+    // squaring with adversarial limb patterns (values need not be < p for the limb-level routine,
+    // only < 2^256 with a^2/R + p < 2^256: keep the top limb small)
+    for (int it = 0; it < 200000; it++) {
+        uint64_t a[4], want[4], got[4];
+        for (int i = 0; i < 4; i++) { uint64_t r = rnd(); a[i] = (r & 1) ? ~0ULL : (r & 2) ? 0 : (r & 4) ? 0xffffffff00000000ULL : rnd(); }
+        a[3] &= 0x3fffffffffffffffULL;
+        if (a[3] > 0x73eda753299d7d47ULL || (a[3] == 0x73eda753299d7d47ULL)) a[3] = 0x73eda753299d7d47ULL;
+        // force canonical (< p): p's top limb is 0x73eda753299d7d48, so top limb <= ...47 suffices
+        hades::Fr fa, fc; to32(fa, a);
+        hades::fr_sqr_lazy(fc, fa);
+        uint32_t r9[9]; for (int k = 0; k < 8; k++) r9[k] = fc.l[k]; r9[8] = 0;
+        hades::canon<0>(fc, r9);
+        to64(got, fc); oracle_fr_mul(a, a, want);
+        if (memcmp(got, want, 32)) { printf("sqr mismatch %d\n", it); return 1; }
+    }
     if (check_perm<5>(300) || check_perm<3>(100) || check_perm<9>(60)) return 1;
     printf("host emulation OK\n");
     return 0;
