@@ -1,0 +1,57 @@
+// This Source Code Form is subject to the terms of the Mozilla Public
+// License, v. 2.0.
+//
+// Raw bindings of libhades_b200.so (C ABI: include/hades_cuda.h).  One `extern` item per symbol the
+// `CudaStrategy` needs; nothing else of the library is bound here.  NOT COMPILED in the build
+// container (no Rust toolchain there): kept mechanical so that it can be checked against the header
+// line by line.
+
+#![allow(non_camel_case_types)]
+
+use core::ffi::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct hades_ctx {
+    _private: [u8; 0],
+}
+
+pub const HADES_OK: c_int = 0;
+
+#[link(name = "hades_b200")]
+extern "C" {
+    // include/hades_cuda.h: hades_init
+    pub fn hades_init(
+        out: *mut *mut hades_ctx,
+        devices: *const c_int,
+        n_dev: c_int,
+        width: u32,
+        ark_limbs: *const u64,
+        n_ark: usize,
+        mds_limbs: *const u64,
+    ) -> c_int;
+    pub fn hades_destroy(ctx: *mut hades_ctx);
+    pub fn hades_last_error(ctx: *const hades_ctx) -> *const c_char;
+    pub fn hades_perm_batch(ctx: *mut hades_ctx, host_states: *mut u64, n: usize) -> c_int;
+    pub fn hades_perm_batch_dev(
+        ctx: *mut hades_ctx,
+        dev_index: c_int,
+        d_states: *mut u64,
+        n: usize,
+        stream: *mut c_void,
+    ) -> c_int;
+    pub fn hades_merkle_root(
+        ctx: *mut hades_ctx,
+        host_leaves: *const u64,
+        n_leaves: usize,
+        root: *mut u64,
+    ) -> c_int;
+    pub fn hades_sponge_batch(
+        ctx: *mut hades_ctx,
+        elems: *const u64,
+        offsets: *const u64,
+        n_msgs: usize,
+        out: *mut u64,
+    ) -> c_int;
+    pub fn hades_host_register(ctx: *mut hades_ctx, ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn hades_host_unregister(ctx: *mut hades_ctx, ptr: *mut c_void) -> c_int;
+}
