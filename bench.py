@@ -182,6 +182,19 @@ class ClockSampler:
         return out
 
 
+def _bind_to_gpu_cpus(index: int):
+    """Pin this rank to the CPUs local to its GPU (NVML's ideal affinity) so that the pinned host
+    buffers of the e2e leg are first-touched on the GPU's NUMA node.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))[:2] + ["..."] + [len(os.sched_getaffinity(0))]
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import numpy as np
@@ -194,6 +207,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = _bind_to_gpu_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -287,7 +301,8 @@ def run_ours(args):
         e2e = {"value": world * ne * e2e_steps / float(el.item()), "unit": UNIT,
                "h2d_bytes_per_step": ne * HBM_BYTES_PER_PERM // 2 * world, "d2h_bytes_per_step": ne * HBM_BYTES_PER_PERM // 2 * world,
                "states_per_gpu_per_step": ne, "steps": e2e_steps, "host_memory": "pinned",
-               "api": "hades_perm_batch (C ABI, chunked H2D/kernel/D2H pipeline)", "gpu_launches": e2e_launches}
+               "api": "hades_perm_batch (C ABI, chunked H2D/kernel/D2H pipeline)", "gpu_launches": e2e_launches,
+               "cpu_affinity": numa}
         del host
 
     cpu_baseline = None
