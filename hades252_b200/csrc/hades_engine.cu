@@ -157,7 +157,7 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
     ctx->ops = width == 3 ? width_ops_3() : width == 5 ? width_ops_5() : width_ops_9();
-    ctx->variant = Variant{1, width == 9 ? 2 : 4};  // W=9 needs 238 registers; others: lockstep 256-thread blocks
+    ctx->variant = Variant{1, width == 9 ? 2 : (width == 5 ? 6 : 4)};  // W=9 needs 238 registers; W=5: lockstep 128x5; W=3: lockstep 256x2
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
     std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
@@ -547,7 +547,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
 }
 
 int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
-    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 5) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
+    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 9) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     ctx->variant = Variant{algo, regs};
     return HADES_OK;
 }

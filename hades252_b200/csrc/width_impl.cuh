@@ -181,9 +181,19 @@ cudaError_t upload(const uint64_t* dense, const uint64_t* opt) {
 
 cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    if (v.algo == 1 && v.regs >= 4) {  // lockstep launches: regs 4 -> 256 threads per block, 5 -> 512
-        if (v.regs == 4) perm_batch_lockstep_kernel<256, 2><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(d_states), n);
-        else perm_batch_lockstep_kernel<512, 1><<<(unsigned)((n + 511) / 512), 512, 0, s>>>(reinterpret_cast<uint4*>(d_states), n);
+    if (v.algo == 1 && v.regs >= 4) {  // lockstep launches: regs 4 -> 256 threads per block, 5 -> 512, 6.. experimental
+        uint4* p = reinterpret_cast<uint4*>(d_states);
+        switch (v.regs) {
+            case 4: perm_batch_lockstep_kernel<256, 2><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n); break;
+            case 5: perm_batch_lockstep_kernel<512, 1><<<(unsigned)((n + 511) / 512), 512, 0, s>>>(p, n); break;
+#if HADES_W == 5
+            case 6: perm_batch_lockstep_kernel<128, 5><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
+            case 7: perm_batch_lockstep_kernel<384, 1><<<(unsigned)((n + 383) / 384), 384, 0, s>>>(p, n); break;
+            case 8: perm_batch_lockstep_kernel<640, 1><<<(unsigned)((n + 639) / 640), 640, 0, s>>>(p, n); break;
+            case 9: perm_batch_lockstep_kernel<128, 4><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
+#endif
+            default: return cudaErrorInvalidValue;
+        }
         return cudaGetLastError();
     }
     size_t blocks = (n + kPermThreads - 1) / kPermThreads;
@@ -229,6 +239,12 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 5) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<512, 1>);
+#if HADES_W == 5
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 5>);
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<384, 1>);
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 8) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<640, 1>);
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 9) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 4>);
+#endif
     if (v.regs >= 4) v.regs = 0;  // merkle / sponge / dense: plain 128-thread launches
     if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);
 #if HADES_W == 5

@@ -12,6 +12,6 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 cat gpurun_out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --log2-states 22 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:perm_batch_kernel -s 1 -c 1 -f -o gpurun_out/prof_perm5 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:perm_batch -s 1 -c 1 -f -o gpurun_out/prof_perm5 \
     python bench.py --steps 1 --warmup 1 --log2-states 22 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out

@@ -11,6 +11,6 @@ print('$v', '%.4g perms/s' % d['value'], 'frac %.3f' % d['roofline']['frac'], 'p
 PY
 done
 V=${NCU_VARIANT:-1,1}
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:perm_batch_kernel -s 1 -c 1 -f -o gpurun_out/prof_perm5 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:perm_batch -s 1 -c 1 -f -o gpurun_out/prof_perm5 \
     python bench.py --steps 1 --warmup 1 --log2-states 22 --no-cpu-baseline --no-e2e --variant $V > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/bench.err
