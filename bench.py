@@ -39,6 +39,9 @@ LIMB_PRODUCTS_PER_PERM = 268192   # 1972 Fr mul x 136 (8-limb CIOS), SURVEY.md 8
 # IMAD.WIDE products the default kernel actually executes per perm:
 #   partial round 2*(36+48) + (64+48) + (5*64+48) + 4*(64+48) = 1096, x59; full round 5*280 + 5*368 = 3240, x8
 EXECUTED_PRODUCTS_PER_PERM = 59 * 1096 + 8 * 3240
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE default-kernel launch over 2^26 states, from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_perm5_2p26_default.txt (10.846 + 10.707 GB)
+NCU_TRAFFIC_BYTES_2P26 = 21_552_500_000
 HBM_BYTES_PER_PERM = 2 * 32 * WIDTH
 SEED = 0x4861646573323532
 METRIC = "hades252_w5_perms_per_sec"
@@ -324,7 +327,11 @@ def run_ours(args):
                        "states_per_gpu": n, "bytes_per_gpu": n * WIDTH * 32, "seed": hex(SEED), "in_place": True,
                        "l2_policy": "inputs (10.7 GB) larger than L2", "parallelism": f"dp{world} (independent states, no collective)"},
             "roofline": {"bound": "int_mul", "achieved": achieved, "peak": p_mul32 / 1e12, "unit": "Tprod/s",
-                         "frac": achieved / (p_mul32 / 1e12), "traffic": None,
+                         "frac": achieved / (p_mul32 / 1e12),
+                         "traffic": NCU_TRAFFIC_BYTES_2P26 if (args.log2_states == 26 and not args.variant) else None,
+                         "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_perm5_2p26_default.txt; algorithmic "
+                                         "bytes per launch = states x 320 B",
+                         "algorithmic_bytes_per_launch": n * HBM_BYTES_PER_PERM,
                          "kernel": "perm_batch_kernel (width 5)", "variant": args.variant or "default", "kernel_ms": kernel_ms,
                          "algorithmic_products_per_perm": LIMB_PRODUCTS_PER_PERM,
                          "executed_products_per_perm": EXECUTED_PRODUCTS_PER_PERM if not args.variant else None,

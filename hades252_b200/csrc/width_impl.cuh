@@ -68,18 +68,64 @@ __global__ void __launch_bounds__(kPermThreads, MINB) perm_batch_kernel(uint4* _
 struct BlockSync {
     static __device__ __forceinline__ void sync() { __syncthreads(); }
 };
+// States are array-of-structs (32*W bytes each), so a per-thread access pattern touches 32 different
+// sectors per warp request.  The lockstep kernel therefore moves a warp's 32 states with fully coalesced
+// 128-bit accesses (lane l moves 16-byte chunks l, l+32, ... of the warp's contiguous 32*32*W bytes) and
+// transposes through shared memory.  Row pitch 2W+1 chunks (176 B at W=5): bank-conflict-free for the
+// per-thread 128-bit reads.
+constexpr int kChunksPerState = 2 * W;
+constexpr int kStagePitch = 2 * W + 1;
+
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) perm_batch_lockstep_kernel(uint4* __restrict__ states, size_t n) {
-    size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    const bool live = i < n;
-    uint4* p = states + (live ? i : n - 1) * (2 * W);
+    constexpr bool kStaged = (size_t)BLOCK * kStagePitch * 16 <= 48 * 1024;
+    __shared__ uint4 stage[kStaged ? BLOCK * kStagePitch : 1];
+    const int lane = threadIdx.x & 31;
+    const size_t warp_first = (size_t)blockIdx.x * BLOCK + (threadIdx.x & ~31);
+    const int n_in_warp = warp_first >= n ? 0 : (n - warp_first < 32 ? (int)(n - warp_first) : 32);
+    const bool live = lane < n_in_warp;
     Fr s[W];
+    if constexpr (kStaged) {
+        uint4* tile = stage + (threadIdx.x & ~31) * kStagePitch;
+        uint4* gbase = states + warp_first * kChunksPerState;
 #pragma unroll
-    for (int j = 0; j < W; j++) fr_load(s[j], p + 2 * j);
-    hades_perm_opt<W, OptTab, BlockSync>(s);
-    if (live) {
+        for (int k = 0; k < kChunksPerState; k++) {
+            const int c = lane + 32 * k, st = c / kChunksPerState, off = c % kChunksPerState;
+            if (st < n_in_warp) tile[st * kStagePitch + off] = gbase[c];
+        }
+        __syncwarp();
+        // dead lanes recompute the warp's first state (or zeros in a fully dead warp) and store nothing
+        const uint4* mine = tile + (live ? lane : 0) * kStagePitch;
 #pragma unroll
-        for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
+        for (int j = 0; j < W; j++) {
+            if (n_in_warp > 0) fr_load(s[j], mine + 2 * j);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) s[j].l[k] = 0;
+            }
+        }
+        __syncwarp();
+        hades_perm_opt<W, OptTab, BlockSync>(s);
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < W; j++) fr_store(tile + lane * kStagePitch + 2 * j, s[j]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kChunksPerState; k++) {
+            const int c = lane + 32 * k, st = c / kChunksPerState, off = c % kChunksPerState;
+            if (st < n_in_warp) gbase[c] = tile[st * kStagePitch + off];
+        }
+    } else {
+        const size_t i = warp_first + lane;
+        uint4* p = states + (i < n ? i : n - 1) * kChunksPerState;
+#pragma unroll
+        for (int j = 0; j < W; j++) fr_load(s[j], p + 2 * j);
+        hades_perm_opt<W, OptTab, BlockSync>(s);
+        if (i < n) {
+#pragma unroll
+            for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
+        }
     }
 }
 
