@@ -157,7 +157,7 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
     ctx->ops = width == 3 ? width_ops_3() : width == 5 ? width_ops_5() : width_ops_9();
-    ctx->variant = Variant{1, width == 9 ? 2 : (width == 5 ? 6 : 4)};  // W=9 needs 238 registers; W=5: lockstep 128x5; W=3: lockstep 256x2
+    ctx->variant = Variant{1, width == 9 ? 7 : 6};  // lockstep 128-thread blocks: x7 (W=3), x5 (W=5), x3 (W=9) per SM
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
     std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);

@@ -163,6 +163,37 @@ merkle_level_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_
     fr_store(out + i * 2, s[1]);
 }
 
+// Lockstep Merkle level: same launch shape as the perm kernel (one barrier per round, no early exit); a
+// warp's 32 x 128 B of children are moved with coalesced 128-bit loads through padded shared memory.
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out) {
+    constexpr int kPitch = 9;  // 8 chunks of children + 1 pad: conflict-free 128-bit reads
+    __shared__ uint4 stage[BLOCK * kPitch];
+    const int lane = threadIdx.x & 31;
+    const size_t warp_first = (size_t)blockIdx.x * BLOCK + (threadIdx.x & ~31);
+    const int n_in_warp = warp_first >= n_out ? 0 : (n_out - warp_first < 32 ? (int)(n_out - warp_first) : 32);
+    const bool live = lane < n_in_warp;
+    uint4* tile = stage + (threadIdx.x & ~31) * kPitch;
+    const uint4* gbase = in + warp_first * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = lane + 32 * k, st = c >> 3, off = c & 7;
+        if (st < n_in_warp) tile[st * kPitch + off] = gbase[c];
+    }
+    __syncwarp();
+    Fr s[5];
+    fr_set_fifteen(s[0]);
+    const uint4* mine = tile + (live ? lane : 0) * kPitch;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (n_in_warp > 0) fr_load(s[1 + j], mine + 2 * j);
+        else fr_set_zero(s[1 + j]);
+    }
+    hades_perm_opt<5, OptTab, BlockSync>(s);
+    if (live) fr_store(out + (warp_first + lane) * 2, s[1]);
+}
+
 // ---- sponge: rate 4 / capacity 1, one message per thread (CSR offsets) ------------------------------
 // `order` (optional) maps thread -> message so that a warp works on messages of equal block count.
 template <int ALGO, int MINB>
@@ -232,6 +263,14 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
         switch (v.regs) {
             case 4: perm_batch_lockstep_kernel<256, 2><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n); break;
             case 5: perm_batch_lockstep_kernel<512, 1><<<(unsigned)((n + 511) / 512), 512, 0, s>>>(p, n); break;
+#if HADES_W == 9
+            case 6: perm_batch_lockstep_kernel<128, 2><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
+            case 7: perm_batch_lockstep_kernel<128, 3><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
+#endif
+#if HADES_W == 3
+            case 6: perm_batch_lockstep_kernel<128, 7><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
+            case 7: perm_batch_lockstep_kernel<128, 5><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
+#endif
 #if HADES_W == 5
             case 6: perm_batch_lockstep_kernel<128, 5><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
             case 7: perm_batch_lockstep_kernel<384, 1><<<(unsigned)((n + 383) / 384), 384, 0, s>>>(p, n); break;
@@ -252,6 +291,11 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
 #if HADES_W == 5
 cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s) {
     if (n_out == 0) return cudaSuccess;
+    if (v.algo == 1 && v.regs >= 4) {  // lockstep launch shapes share one Merkle build
+        merkle_level_lockstep_kernel<128, 5><<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(
+            reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out);
+        return cudaGetLastError();
+    }
     if (v.regs >= 4) v.regs = 0;
     size_t blocks = (n_out + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
@@ -285,13 +329,24 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 5) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<512, 1>);
+#if HADES_W == 9
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 2>);
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 3>);
+#endif
+#if HADES_W == 3
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 7>);
+    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 5>);
+#endif
 #if HADES_W == 5
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 5>);
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<384, 1>);
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 8) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<640, 1>);
     if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 9) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 4>);
 #endif
-    if (v.regs >= 4) v.regs = 0;  // merkle / sponge / dense: plain 128-thread launches
+#if HADES_W == 5
+    if (!strcmp(kernel, "merkle") && v.algo == 1 && v.regs >= 4) return cudaFuncGetAttributes(out, merkle_level_lockstep_kernel<128, 5>);
+#endif
+    if (v.regs >= 4) v.regs = 0;  // sponge / dense: plain 128-thread launches
     if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);
 #if HADES_W == 5
     if (!strcmp(kernel, "merkle")) return HADES_ATTR(merkle_level_kernel, v, out);

@@ -12,7 +12,9 @@ namespace hades {
 //   algo 0 = dense schedule (reference round structure, one lazily reduced dot product per MDS row)
 //   algo 1 = optimised schedule (sparse partial rounds, host_tables.hpp)
 //   regs 0 = __launch_bounds__(128, 4) (<=128 registers), 1 = (128, 3) (<=168), 2 = (128, 2) (<=255),
-//   3 = (128, 5) (<=96); 4 / 5 = lockstep blocks of 256 / 512 threads with one barrier per round
+//   3 = (128, 5) (<=96); 4 / 5 = lockstep blocks of 256 / 512 threads with one barrier per round;
+//   6.. = lockstep 128-thread blocks (W=5: 6 -> 5 blocks/SM [default], 9 -> 4; W=3: 6 -> 7 [default], 7 -> 5;
+//   W=9: 6 -> 2, 7 -> 3 [default]); 7/8 at W=5 are 384/640-thread experiments
 //   (optimised perm kernel only; keeps the warps of a block on the same instruction-cache lines)
 struct Variant {
     int algo;

@@ -300,3 +300,77 @@ def test_large_batch_digest_property(cuda_strategy, oracle):
         torch.cuda.synchronize()
         digs.append(dig.cpu().numpy().copy())
     assert np.array_equal(digs[0], digs[1])
+
+
+def test_cuda_graph_capture_of_device_calls(cuda_strategy, oracle):
+    """The device-resident entry points only enqueue work on the caller's stream, so a whole Merkle
+    reduction (6 level launches) and a perm_batch can be captured in a CUDA graph and replayed."""
+    import torch
+    n = 4 ** 6
+    leaves = oracle.gen_elems(99, n)
+    d = torch.from_numpy(leaves.view(np.int64).copy()).cuda()
+    scratch = torch.empty((n // 4 + n // 16 + 4) * 4, dtype=torch.int64, device="cuda")
+    out = torch.zeros(4, dtype=torch.int64, device="cuda")
+    states = torch.from_numpy(oracle.gen_elems(5, 5 * 512).view(np.int64).copy()).cuda()
+    s0 = states.clone()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        cuda_strategy.merkle_reduce_device(d.data_ptr(), n, 6, scratch.data_ptr(), out.data_ptr(), side.cuda_stream)  # warm-up
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            cuda_strategy.merkle_reduce_device(d.data_ptr(), n, 6, scratch.data_ptr(), out.data_ptr(), side.cuda_stream)
+            cuda_strategy.perm_batch_device(states.data_ptr(), 512, side.cuda_stream)
+    out.zero_()
+    states.copy_(s0)
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), oracle.merkle_root(leaves))
+    want = oracle.perm_batch(s0.cpu().numpy().view(np.uint64).reshape(512, 5, 4))
+    assert np.array_equal(states.cpu().numpy().view(np.uint64).reshape(512, 5, 4), want)
+    g.replay()  # second replay permutes the permuted states again
+    torch.cuda.synchronize()
+    assert np.array_equal(states.cpu().numpy().view(np.uint64).reshape(512, 5, 4), oracle.perm_batch(want))
+
+
+def test_host_register_path(cuda_strategy, oracle):
+    n = 50000
+    s = oracle.gen_elems(8, 5 * n).reshape(n, 5, 4)
+    got = s.copy()
+    cuda_strategy.host_register(got.ctypes.data, got.nbytes)
+    try:
+        cuda_strategy.perm_batch(got)
+    finally:
+        cuda_strategy.host_unregister(got.ctypes.data)
+    assert np.array_equal(got, oracle.perm_batch(s))
+
+
+def test_concurrent_contexts_from_threads(oracle):
+    """One context per caller thread (the `&mut self` contract); contexts may run concurrently."""
+    import threading
+    from hades252_b200 import CudaStrategy
+    n = 20000
+    inputs = [oracle.gen_elems(1000 * t, 5 * n).reshape(n, 5, 4) for t in range(4)]
+    outs = [None] * 4
+
+    def work(t):
+        with CudaStrategy([0]) as strat:
+            o = inputs[t].copy()
+            for _ in range(2):
+                strat.perm_batch(o)
+            outs[t] = o
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for t in range(4):
+        assert np.array_equal(outs[t], oracle.perm_batch(oracle.perm_batch(inputs[t])))
+
+
+def test_permutation_is_a_bijection_on_a_sample(cuda_strategy, oracle):
+    """Size-independent property: distinct inputs give distinct outputs (2^16 states)."""
+    n = 1 << 16
+    s = oracle.gen_elems(31, 5 * n).reshape(n, 5, 4)
+    o = s.copy()
+    cuda_strategy.perm_batch(o)
+    assert len({bytes(x) for x in o.reshape(n, -1)}) == n
