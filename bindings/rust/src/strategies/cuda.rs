@@ -135,36 +135,31 @@ impl Drop for CudaStrategy {
     }
 }
 
-/// `Strategy::perm` on one state is a batch of one.  The round primitives of the trait are not
-/// used by the device path (the whole permutation is one kernel), so they delegate to the same
-/// field operations as `ScalarStrategy` to keep the trait contract intact for generic callers.
+/// `Strategy::perm` on one state is a batch of one: the whole permutation is a single kernel, so
+/// the per-round primitives of the trait are never called by the device path.  They are still part
+/// of the trait contract, so they forward to `ScalarStrategy` (same field operations) for generic
+/// callers that drive rounds by hand.
 impl Strategy<BlsScalar> for CudaStrategy {
     fn add_round_key<'b, I>(&mut self, constants: &mut I, words: &mut [BlsScalar])
     where
         I: Iterator<Item = &'b BlsScalar>,
     {
-        words.iter_mut().for_each(|w| *w += Self::next_c(constants));
+        super::ScalarStrategy::new().add_round_key(constants, words)
     }
 
     fn quintic_s_box(&mut self, value: &mut BlsScalar) {
-        *value = value.square().square() * *value;
+        super::ScalarStrategy::new().quintic_s_box(value)
     }
 
-    fn mul_matrix<'b, I>(&mut self, _constants: &mut I, values: &mut [BlsScalar])
+    fn mul_matrix<'b, I>(&mut self, constants: &mut I, values: &mut [BlsScalar])
     where
         I: Iterator<Item = &'b BlsScalar>,
     {
-        let mut result = [BlsScalar::zero(); WIDTH];
-        for (j, value) in values.iter().enumerate().take(WIDTH) {
-            for k in 0..WIDTH {
-                result[k] += MDS_MATRIX[k][j] * value;
-            }
-        }
-        values.copy_from_slice(&result);
+        super::ScalarStrategy::new().mul_matrix(constants, values)
     }
 
     fn perm(&mut self, data: &mut [BlsScalar]) {
-        // same programmer-error behaviour as the reference (scalar.rs:48 `copy_from_slice` panics)
+        // same programmer-error behaviour as the reference: a length other than WIDTH panics
         let state: &mut [BlsScalar; WIDTH] =
             data.try_into().expect("Hades252 perm needs exactly WIDTH scalars");
         self.perm_batch(core::slice::from_mut(state))

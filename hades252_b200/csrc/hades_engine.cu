@@ -547,7 +547,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
 }
 
 int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
-    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 9) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
+    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 10) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     ctx->variant = Variant{algo, regs};
     return HADES_OK;
 }

@@ -276,6 +276,7 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
             case 7: perm_batch_lockstep_kernel<384, 1><<<(unsigned)((n + 383) / 384), 384, 0, s>>>(p, n); break;
             case 8: perm_batch_lockstep_kernel<640, 1><<<(unsigned)((n + 639) / 640), 640, 0, s>>>(p, n); break;
             case 9: perm_batch_lockstep_kernel<128, 4><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
+            case 10: perm_batch_lockstep_kernel<128, 6><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, n); break;
 #endif
             default: return cudaErrorInvalidValue;
         }
