@@ -391,14 +391,21 @@ HADES_DEV void dot_step(uint32_t (&E)[9], uint32_t (&O)[9], uint32_t x, int i, V
     redc_even(E, m);
 }
 
-template <int N, class Vec, class Sca>
-HADES_DEV void dot_mont(uint32_t (&r)[9], Vec vec, Sca sca) {
+// STEPS outer steps (even): r = (sum_j A_j * B_j[0..STEPS)) / 2^(32*STEPS), where B_j is consumed
+// STEPS limbs deep.  STEPS = 8 is the ordinary Montgomery product (R = 2^256).  Smaller STEPS implement
+// the SHORT reduction used for multiplications by constants: y = sum_j y_j 2^(32*STEPS*j) and the
+// constants X_j = c * 2^(32*STEPS*(j+1) - 256) mod p are precomputed on the host, so
+//     sum_j X_j * y_j / 2^(32*STEPS)  ==  c * y / 2^256   (mod p)
+// with the same 64 limb products but only 6*STEPS reduction products instead of 48.
+template <int N, int STEPS, class Vec, class Sca>
+HADES_DEV void dot_mont_steps(uint32_t (&r)[9], Vec vec, Sca sca) {
+    static_assert(STEPS == 2 || STEPS == 4 || STEPS == 8, "even/odd bookkeeping needs an even step count");
     uint32_t A[9], B[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) A[k] = B[k] = 0;
     uint32_t x = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
+    for (int i = 0; i < STEPS; i += 2) {
         // step i: E = A, O = B
         if (i == 0) dot_step<N, true>(A, B, 0u, i, vec, sca);
         else dot_step<N, false>(A, B, x, i, vec, sca);
@@ -414,8 +421,22 @@ HADES_DEV void dot_mont(uint32_t (&r)[9], Vec vec, Sca sca) {
         for (int k = 0; k < 7; k++) B[k] = B[k + 2];
         B[7] = 0; B[8] = 0;
     }
-    // after 8 steps: E = A (positions 0..8), O = B (positions 1..9), pending x at position 0
+    // after the steps: E = A (positions 0..8), O = B (positions 1..9), pending x at position 0
     merge_even_odd(r, A, B, x);
+}
+
+template <int N, class Vec, class Sca>
+HADES_DEV void dot_mont(uint32_t (&r)[9], Vec vec, Sca sca) {
+    dot_mont_steps<N, 8>(r, vec, sca);
+}
+
+// r = c * y / 2^256 (mod p, < 5p for K = 4, < 3p for K = 2) for a constant c given as its K short-reduction
+// versions: xk(j, limb) = limb of X_j = c * 2^(256*(j+1)/K - 256) mod p, j = 0..K-1.
+template <int K, class XK>
+HADES_DEV void mul_const_short(uint32_t (&r)[9], XK xk, const Fr& y) {
+    constexpr int kSteps = 8 / K;
+    dot_mont_steps<K, kSteps>(
+        r, [&](int j, int limb) { return xk(j, limb); }, [&](int j, int i) { return y.l[j * kSteps + i]; });
 }
 
 // ------------------------------------------------------------------------------------------------

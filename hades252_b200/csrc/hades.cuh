@@ -85,7 +85,7 @@ HADES_DEV void hades_perm(Fr (&s)[W]) {
 // canonical, so the results are bit-identical to `Strategy::perm`.
 //
 // `T` is a table policy:  uint32_t T::tab(int entry, int limb)  over the layout of host_tables.hpp:
-//   [0, 8W) full-round ARK | MDS (W*W) | PRE (W*W) | C4' (W) | 59 x { e, d, b[W-1], chat[W-1] }
+//   [0, 8W) full-round ARK | MDS (W*W) | PRE (W*W) | C4' (W) | 59 x { e, d, chat[W-1], K versions of each b[W-1] }
 // ------------------------------------------------------------------------------------------------
 template <int W>
 struct OptLayout {
@@ -94,7 +94,8 @@ struct OptLayout {
     static constexpr int kPre = kMds + W * W;
     static constexpr int kC4 = kPre + W * W;
     static constexpr int kSparse = kC4 + W;
-    static constexpr int kSparseStride = 2 * W;
+    static constexpr int kShort = (W <= 5) ? 4 : 1;  // short-reduction versions per b constant (host_tables.hpp)
+    static constexpr int kSparseStride = 2 + (W - 1) + kShort * (W - 1);
     static constexpr int kEntries = kSparse + kPartialRounds * kSparseStride;
 };
 
@@ -180,21 +181,22 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
     {
         uint32_t r[9];
         dot_mont<W>(
-            r, [&](int j, int k) { return j < t ? T::tab(base + 2 + t + j, k) : T::tab(base + 1, k); },
+            r, [&](int j, int k) { return j < t ? T::tab(base + 2 + j, k) : T::tab(base + 1, k); },
             [&](int j, int i) { return j < t ? s[j].l[i] : y.l[i]; });
         canon<(W <= 5) ? 1 : 2>(s[t], r);
     }
-    // w_i += b_i * y :  product < 1.854p, plus w_i < p  =>  < 2.854p < 4p.  t trips on word 0, rotating
-    // the first t words (after t trips they are back in place).
+    // w_i += b_i * y with the SHORT reduction (fr.cuh mul_const_short): K = 4 versions of b_i, y consumed
+    // in four 64-bit pieces, 64 + 12 products instead of 64 + 48.  Bound: < 5p (K = 4) or < 1.854p (K = 1),
+    // plus w_i < p  =>  < 6p < 8p.  t trips on word 0, rotating the first t words (back in place after t).
     Fr w[t];
 #pragma unroll
     for (int i = 0; i < t; i++) w[i] = s[i];
     HADES_NO_UNROLL
     for (int i = 0; i < t; i++) {
         uint32_t q[9];
-        const int bi = base + 2 + i;
-        dot_mont<1>(
-            q, [&](int, int k) { return T::tab(bi, k); }, [&](int, int limb) { return y.l[limb]; });
+        constexpr int K = OptLayout<W>::kShort;
+        const int bi = base + 2 + t + K * i;
+        mul_const_short<K>(q, [&](int j, int k) { return T::tab(bi + j, k); }, y);
         uint32_t sum[9], q8[8], lo[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) q8[k] = q[k];
@@ -203,7 +205,7 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
         for (int k = 0; k < 8; k++) sum[k] = lo[k];
         sum[8] = q[8] + c;
         Fr res;
-        canon<1>(res, sum);
+        canon<(OptLayout<W>::kShort > 1) ? 2 : 1>(res, sum);
         rotate_in<t>(w, res);
     }
 #pragma unroll

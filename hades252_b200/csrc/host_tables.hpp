@@ -22,7 +22,10 @@
 //   [F*W,          +W*W)       MDS   (dense M, row-major)
 //   [..,           +W*W)       PRE   (dense M'_0 * M, used by full round 3)
 //   [..,           +W)         C4'   (M'_0 * c_4, added to every word before the first partial round)
-//   [..,           +Q*2W)      per partial round q: e_q, d_q, b_q[0..W-2], chat_q[0..W-2]
+//   [..,           +Q*stride)  per partial round q: e_q, d_q, chat_q[0..W-2], then for every b_q[i] its K
+//                              short-reduction versions X_j = b * 2^(256 (j+1)/K - 256), j = 0..K-1
+//                              (fr.cuh mul_const_short); stride = 2 + (W-1) + K (W-1).  K = 4 for W <= 5,
+//                              K = 1 (the plain constant) for wider states (constant-memory budget).
 #pragma once
 #include <stdint.h>
 
@@ -166,7 +169,9 @@ inline bool invert(const Mat& A, Mat& out) {
 
 constexpr int kFull = 8, kPartial = 59, kHalf = 4;
 
-inline size_t table_entries(int W) { return (size_t)kFull * W + 2 * (size_t)W * W + W + (size_t)kPartial * 2 * W; }
+inline int short_versions(int W) { return W <= 5 ? 4 : 1; }
+inline size_t sparse_stride(int W) { return 2 + (size_t)(W - 1) + (size_t)short_versions(W) * (W - 1); }
+inline size_t table_entries(int W) { return (size_t)kFull * W + 2 * (size_t)W * W + W + (size_t)kPartial * sparse_stride(W); }
 
 // ark: >= 67*W entries, mds: W*W entries (Montgomery limbs).  out: table_entries(W)*4 u64.
 inline bool derive_tables(int W, const uint64_t* ark, const uint64_t* mds, std::vector<uint64_t>& out) {
@@ -223,11 +228,21 @@ inline bool derive_tables(int W, const uint64_t* ark, const uint64_t* mds, std::
     for (int i = 0; i < W; i++)
         for (int j = 0; j < W; j++) put(D[i][j]);
     for (int j = 0; j < W; j++) put(c4[j]);
+    const int K = short_versions(W);
+    // mul(a, 2^(256 - 256/K) as a plain integer) = a * 2^(-256/K): one step down the version ladder
+    F down = kZero;
+    if (K == 4) down.l[3] = 1;            // 2^192
+    else if (K == 2) down.l[2] = 1;       // 2^128
     for (int q = 0; q < kPartial; q++) {
         put(e[q]);
         put(sp[q].dd);
-        for (int i = 0; i < t; i++) put(sp[q].b[i]);
         for (int i = 0; i < t; i++) put(sp[q].chat[i]);
+        for (int i = 0; i < t; i++) {
+            F ver[4];
+            ver[K - 1] = sp[q].b[i];
+            for (int j = K - 2; j >= 0; j--) ver[j] = mul(ver[j + 1], down);
+            for (int j = 0; j < K; j++) put(ver[j]);
+        }
     }
     return out.size() == table_entries(W) * 4;
 }
