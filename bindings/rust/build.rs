@@ -10,7 +10,10 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from("cuda/csrc"); // = hades252_b200/csrc of the engine repository
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    let units = ["hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu"];
+    let units = [
+        "hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu", "hades_w3_dense.cu", "hades_w5_dense.cu",
+        "hades_w9_dense.cu",
+    ];
     let mut objs = Vec::new();
     for u in units {
         let obj = out.join(u.replace(".cu", ".o"));

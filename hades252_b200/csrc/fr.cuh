@@ -338,18 +338,26 @@ HADES_DEV void cond_sub_p_shl(uint32_t (&x)[8], uint32_t& x8) {
 }
 
 // r (9 limbs, value < 2^(LOG2+1) * p... precisely value < 2p << LOG2) -> canonical [0,p).
-// LOG2 = 0: value < 2p; 1: < 4p; 2: < 8p.
+// LOG2 = 0: value < 2p; 1: < 4p; 2: < 8p; 3: < 16p; 4: < 32p (all fit the 9 limbs).
 template <int LOG2>
 HADES_DEV void canon(Fr& out, const uint32_t (&r)[9]) {
+    static_assert(LOG2 >= 0 && LOG2 <= 4, "bound out of range");
     uint32_t x[8], x8 = r[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) x[k] = r[k];
+    if constexpr (LOG2 >= 4) cond_sub_p_shl<4>(x, x8);
+    if constexpr (LOG2 >= 3) cond_sub_p_shl<3>(x, x8);
     if constexpr (LOG2 >= 2) cond_sub_p_shl<2>(x, x8);
     if constexpr (LOG2 >= 1) cond_sub_p_shl<1>(x, x8);
     cond_sub_p_shl<0>(x, x8);
     HADES_ASSERT(x8 == 0);
 #pragma unroll
     for (int k = 0; k < 8; k++) out.l[k] = x[k];
+}
+
+// smallest LOG2 such that a value < bound_p * p is below 2p << LOG2
+HADES_DEV constexpr int canon_log2_for(int bound_p) {
+    return bound_p <= 2 ? 0 : bound_p <= 4 ? 1 : bound_p <= 8 ? 2 : bound_p <= 16 ? 3 : 4;
 }
 
 // out = a + b mod p, inputs canonical (scalar.rs:28 `*w += c`)

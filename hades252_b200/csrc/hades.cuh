@@ -85,17 +85,34 @@ HADES_DEV void hades_perm(Fr (&s)[W]) {
 // canonical, so the results are bit-identical to `Strategy::perm`.
 //
 // `T` is a table policy:  uint32_t T::tab(int entry, int limb)  over the layout of host_tables.hpp:
-//   [0, 8W) full-round ARK | MDS (W*W) | PRE (W*W) | C4' (W) | 59 x { e, d, chat[W-1], K versions of each b[W-1] }
+//   [0, 8W) full-round ARK | MDS (W*W*KR) | PRE (W*W*KR) | C4' (W) | 59 x { e, d*KD, chat[W-1]*KD, b[W-1]*KB }
+// (K* = short-reduction versions per constant, OptLayout)
 // ------------------------------------------------------------------------------------------------
+// Short-reduction versions (fr.cuh mul_const_short / dot_mont_steps) kept per constant: the more
+// versions, the fewer reduction products (6 * 8/K per reduction instead of 48) but the more constant
+// memory and the larger the bound to canonicalise.  Chosen per width to fit the 64 KB constant bank.
 template <int W>
 struct OptLayout {
+#if defined(HADES_KB) && defined(HADES_KR) && defined(HADES_KD)  // tuning overrides (tools/)
+    static constexpr int kShortB = HADES_KB, kShortRow = HADES_KR, kShortDot = HADES_KD;
+#else
+    // Measured on B200 (W = 5): K > 1 on the multi-term rows / dot product needs more than the 63 uniform
+    // registers for the constants of one step, spills, and loses 10-20 %; on the single-term b products
+    // K = 4 is a clear win (+9.5 %).
+    static constexpr int kShortB = (W <= 5) ? 4 : 2;  // b constants of the sparse rounds
+    static constexpr int kShortRow = 1;               // dense rows (MDS, PRE) of the full rounds
+    static constexpr int kShortDot = 1;               // chat / d of the sparse rounds
+#endif
     static constexpr int kArk = 0;
     static constexpr int kMds = kFullRounds * W;
-    static constexpr int kPre = kMds + W * W;
-    static constexpr int kC4 = kPre + W * W;
+    static constexpr int kPre = kMds + W * W * kShortRow;
+    static constexpr int kC4 = kPre + W * W * kShortRow;
     static constexpr int kSparse = kC4 + W;
-    static constexpr int kShort = (W <= 5) ? 4 : 1;  // short-reduction versions per b constant (host_tables.hpp)
-    static constexpr int kSparseStride = 2 + (W - 1) + kShort * (W - 1);
+    // per sparse round: e | d (kShortDot) | chat[W-1] (kShortDot each) | b[W-1] (kShortB each)
+    static constexpr int kSparseD = 1;
+    static constexpr int kSparseChat = kSparseD + kShortDot;
+    static constexpr int kSparseB = kSparseChat + (W - 1) * kShortDot;
+    static constexpr int kSparseStride = kSparseB + (W - 1) * kShortB;
     static constexpr int kEntries = kSparse + kPartialRounds * kSparseStride;
 };
 
@@ -148,12 +165,18 @@ HADES_DEV void full_round_opt(Fr (&s)[W], int ark, int mat) {
     for (int j = 0; j < W; j++) out[j] = s[j];  // placeholder values, all W get overwritten
     HADES_NO_UNROLL
     for (int row = 0; row < W; row++) {
+        // row = sum_j M[row][j] * s_j with the short reduction: every constant has KR versions and every
+        // s_j is consumed in KR pieces: W*KR terms, 8/KR steps.  Bound: W*KR terms of (< p) * (< 2^(256/KR))
+        // => < (W*KR + 1) p.
+        constexpr int KR = OptLayout<W>::kShortRow;
+        constexpr int kSteps = 8 / KR;
         uint32_t r[9];
-        const int base = mat + row * W;
-        dot_mont<W>(
-            r, [&](int j, int k) { return T::tab(base + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+        const int base = mat + row * W * KR;
+        dot_mont_steps<W * KR, kSteps>(
+            r, [&](int jj, int k) { return T::tab(base + jj, k); },
+            [&](int jj, int i) { return s[jj / KR].l[(jj % KR) * kSteps + i]; });
         Fr res;
-        canon<(W <= 6) ? 1 : 2>(res, r);
+        canon<canon_log2_for(W * KR + 1)>(res, r);
         rotate_in<W>(out, res);
     }
 #pragma unroll
@@ -179,23 +202,32 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
     // new last word = sum_{j<t} chat_j * w_j + d * y  (uses the OLD w_j)
     // bound: (t + 1.886) p^2  =>  < p (1 + 0.4528 (t + 1.886)): W=5 -> 3.67p, W=9 -> 5.48p
     {
+        // terms: (chat_j, w_j) for j < t and (d, y); each constant in KD short-reduction versions.
+        // Bound: KD = 1: (t + 1.886) * 0.4528 + 1 (< 4p at W = 5, < 8p at W = 9); KD > 1: < (W*KD + 1) p.
+        typedef OptLayout<W> L;
+        constexpr int KD = L::kShortDot;
+        constexpr int kSteps = 8 / KD;
         uint32_t r[9];
-        dot_mont<W>(
-            r, [&](int j, int k) { return j < t ? T::tab(base + 2 + j, k) : T::tab(base + 1, k); },
-            [&](int j, int i) { return j < t ? s[j].l[i] : y.l[i]; });
-        canon<(W <= 5) ? 1 : 2>(s[t], r);
+        dot_mont_steps<W * KD, kSteps>(
+            r,
+            [&](int jj, int k) {
+                return (jj / KD) < t ? T::tab(base + L::kSparseChat + jj, k) : T::tab(base + L::kSparseD + (jj % KD), k);
+            },
+            [&](int jj, int i) {
+                return (jj / KD) < t ? s[jj / KD].l[(jj % KD) * kSteps + i] : y.l[(jj % KD) * kSteps + i];
+            });
+        canon<(KD == 1) ? ((W <= 5) ? 1 : 2) : canon_log2_for(W * KD + 1)>(s[t], r);
     }
-    // w_i += b_i * y with the SHORT reduction (fr.cuh mul_const_short): K = 4 versions of b_i, y consumed
-    // in four 64-bit pieces, 64 + 12 products instead of 64 + 48.  Bound: < 5p (K = 4) or < 1.854p (K = 1),
-    // plus w_i < p  =>  < 6p < 8p.  t trips on word 0, rotating the first t words (back in place after t).
+    // w_i += b_i * y with the SHORT reduction (fr.cuh mul_const_short): K versions of b_i, y consumed in K
+    // pieces: 64 + 48/K products instead of 64 + 48.  Bound: < (K + 1) p, plus w_i < p.  t trips on word 0, rotating the first t words (back in place after t).
     Fr w[t];
 #pragma unroll
     for (int i = 0; i < t; i++) w[i] = s[i];
     HADES_NO_UNROLL
     for (int i = 0; i < t; i++) {
         uint32_t q[9];
-        constexpr int K = OptLayout<W>::kShort;
-        const int bi = base + 2 + t + K * i;
+        constexpr int K = OptLayout<W>::kShortB;
+        const int bi = base + OptLayout<W>::kSparseB + K * i;
         mul_const_short<K>(q, [&](int j, int k) { return T::tab(bi + j, k); }, y);
         uint32_t sum[9], q8[8], lo[8];
 #pragma unroll
@@ -205,7 +237,7 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
         for (int k = 0; k < 8; k++) sum[k] = lo[k];
         sum[8] = q[8] + c;
         Fr res;
-        canon<(OptLayout<W>::kShort > 1) ? 2 : 1>(res, sum);
+        canon<canon_log2_for(OptLayout<W>::kShortB + 2)>(res, sum);  // < (K + 1) p + w_i
         rotate_in<t>(w, res);
     }
 #pragma unroll

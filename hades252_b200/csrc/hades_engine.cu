@@ -42,7 +42,8 @@ thread_local std::string g_init_error;
 
 struct hades_ctx {
     uint32_t width = 0;
-    const WidthOps* ops = nullptr;
+    const WidthOps* ops2[2] = {nullptr, nullptr};  // [algo]
+    const WidthOps* ops() const { return ops2[variant.algo]; }
     Variant variant = {1, 0};  // optimised schedule, <=128 registers
     std::vector<DeviceState> devs;
     mutable std::string err;
@@ -87,7 +88,8 @@ int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dens
                         "constant tables for width %u already resident on device %d with different contents", ctx->width, ordinal);
         return HADES_OK;
     }
-    CUDA_TRY(ctx, ctx->ops->upload(dense.data(), opt.data()));
+    CUDA_TRY(ctx, ctx->ops2[0]->upload(dense.data()));
+    CUDA_TRY(ctx, ctx->ops2[1]->upload(opt.data()));
     g_tables[{ordinal, (int)ctx->width}] = dense;
     return HADES_OK;
 }
@@ -95,7 +97,7 @@ int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dens
 int launch_perm_w(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t stream) {
     if (n == 0) return HADES_OK;
     ctx->launches++;
-    CUDA_TRY(ctx, ctx->ops->launch_perm(ctx->variant, d_states, n, stream));
+    CUDA_TRY(ctx, ctx->ops()->launch_perm(ctx->variant, d_states, n, stream));
     return HADES_OK;
 }
 
@@ -121,7 +123,7 @@ int merkle_reduce(hades_ctx* ctx, const uint64_t* d_nodes, size_t n_nodes, int l
         size_t n_out = n / 4;
         uint64_t* out = (l == levels - 1) ? d_out : ((l & 1) ? bufB : bufA);
         ctx->launches++;
-        CUDA_TRY(ctx, ctx->ops->launch_merkle_level(ctx->variant, in, out, n_out, stream));
+        CUDA_TRY(ctx, ctx->ops()->launch_merkle_level(ctx->variant, in, out, n_out, stream));
         in = out;
         n = n_out;
     }
@@ -156,14 +158,14 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
-    ctx->ops = width == 3 ? width_ops_3() : width == 5 ? width_ops_5() : width_ops_9();
+    for (int a = 0; a < 2; a++) ctx->ops2[a] = width == 3 ? width_ops_3(a) : width == 5 ? width_ops_5(a) : width_ops_9(a);
     ctx->variant = Variant{1, width == 9 ? 7 : 6};  // lockstep 128-thread blocks: x7 (W=3), x5 (W=5), x3 (W=9) per SM
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
     std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
     int rc = HADES_OK;
-    if (dense.size() != ctx->ops->dense_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
-    if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops->opt_u64))
+    if (dense.size() != ctx->ops2[0]->table_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
+    if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops2[1]->table_u64))
         rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the sparse partial-round tables (singular MDS sub-matrix)");
     for (int g = 0; g < n_dev && rc == HADES_OK; g++) {
         DeviceState d;
@@ -391,7 +393,7 @@ int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elem
     CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
     ctx->launches++;
     int rc = HADES_OK;
-    cudaError_t e = ctx->ops->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, st);
+    cudaError_t e = ctx->ops()->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, st);
     if (e != cudaSuccess) rc = fail(ctx, HADES_ERR_CUDA, "sponge launch failed: %s", cudaGetErrorString(e));
     cudaFreeAsync(keys, st); cudaFreeAsync(keys_out, st); cudaFreeAsync(idx, st); cudaFreeAsync(order, st); cudaFreeAsync(tmp, st);
     return rc;
@@ -537,7 +539,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
     if (!ctx || !kernel) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
     cudaFuncAttributes a;
-    cudaError_t e = ctx->ops->func_attributes(kernel, ctx->variant, &a);
+    cudaError_t e = ctx->ops()->func_attributes(kernel, ctx->variant, &a);
     if (e == cudaErrorInvalidValue) return fail(ctx, HADES_ERR_INVALID_ARG, "unknown kernel '%s' for width %u", kernel, ctx->width);
     CUDA_TRY(ctx, e);
     if (regs_per_thread) *regs_per_thread = a.numRegs;

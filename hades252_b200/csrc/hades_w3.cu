@@ -1,6 +1,7 @@
-// Width-3 kernels of the Hades252 engine (own translation unit = own 64 KB __constant__ bank).
+// Width-3 kernels, optimised schedule (own translation unit = own 64 KB __constant__ bank).
 #define HADES_W 3
+#define HADES_ALGO 1
 #include "width_impl.cuh"
 namespace hades {
-const WidthOps* width_ops_3() { return &kOps; }
+const WidthOps* width_ops_3_opt() { return &kOps; }
 }  // namespace hades

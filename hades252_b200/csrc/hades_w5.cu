@@ -1,6 +1,7 @@
-// Width-5 kernels of the Hades252 engine (own translation unit = own 64 KB __constant__ bank).
+// Width-5 kernels, optimised schedule (own translation unit = own 64 KB __constant__ bank).
 #define HADES_W 5
+#define HADES_ALGO 1
 #include "width_impl.cuh"
 namespace hades {
-const WidthOps* width_ops_5() { return &kOps; }
+const WidthOps* width_ops_5_opt() { return &kOps; }
 }  // namespace hades

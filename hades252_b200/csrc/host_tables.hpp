@@ -19,13 +19,14 @@
 //
 // Table layout (entries of 4 u64 Montgomery limbs), W = width, F = 8 full rounds, Q = 59:
 //   [0,            F*W)        ARK of the full rounds: rounds 0..3, then c63' = c_63 + M d_58, c_64..c_66
-//   [F*W,          +W*W)       MDS   (dense M, row-major)
-//   [..,           +W*W)       PRE   (dense M'_0 * M, used by full round 3)
+//   [F*W,          +W*W*KR)    MDS   (dense M, row-major, KR short-reduction versions per entry)
+//   [..,           +W*W*KR)    PRE   (dense M'_0 * M, used by full round 3; same)
 //   [..,           +W)         C4'   (M'_0 * c_4, added to every word before the first partial round)
-//   [..,           +Q*stride)  per partial round q: e_q, d_q, chat_q[0..W-2], then for every b_q[i] its K
-//                              short-reduction versions X_j = b * 2^(256 (j+1)/K - 256), j = 0..K-1
-//                              (fr.cuh mul_const_short); stride = 2 + (W-1) + K (W-1).  K = 4 for W <= 5,
-//                              K = 1 (the plain constant) for wider states (constant-memory budget).
+//   [..,           +Q*stride)  per partial round q: e_q | d_q (KD versions) | chat_q[0..W-2] (KD each) |
+//                              b_q[0..W-2] (KB each).  "K versions" of a constant c are the short-reduction
+//                              constants X_j = c * 2^(256 (j+1)/K - 256), j = 0..K-1 (fr.cuh dot_mont_steps):
+//                              the product is then reduced in 8/K steps instead of 8.  K per width is chosen
+//                              to fit the 64 KB constant bank (short_b / short_row / short_dot below).
 #pragma once
 #include <stdint.h>
 
@@ -169,9 +170,14 @@ inline bool invert(const Mat& A, Mat& out) {
 
 constexpr int kFull = 8, kPartial = 59, kHalf = 4;
 
-inline int short_versions(int W) { return W <= 5 ? 4 : 1; }
-inline size_t sparse_stride(int W) { return 2 + (size_t)(W - 1) + (size_t)short_versions(W) * (W - 1); }
-inline size_t table_entries(int W) { return (size_t)kFull * W + 2 * (size_t)W * W + W + (size_t)kPartial * sparse_stride(W); }
+// short-reduction versions per constant; must match OptLayout<W> in hades.cuh (checked in the emulation test)
+inline int short_b(int W) { return W <= 5 ? 4 : 2; }
+inline int short_row(int) { return 1; }
+inline int short_dot(int) { return 1; }
+inline size_t sparse_stride(int W) { return 1 + (size_t)short_dot(W) * W + (size_t)short_b(W) * (W - 1); }
+inline size_t table_entries(int W) {
+    return (size_t)kFull * W + 2 * (size_t)W * W * short_row(W) + W + (size_t)kPartial * sparse_stride(W);
+}
 
 // ark: >= 67*W entries, mds: W*W entries (Montgomery limbs).  out: table_entries(W)*4 u64.
 inline bool derive_tables(int W, const uint64_t* ark, const uint64_t* mds, std::vector<uint64_t>& out) {
@@ -223,26 +229,27 @@ inline bool derive_tables(int W, const uint64_t* ark, const uint64_t* mds, std::
     for (int j = 0; j < W; j++) put(add(c[kHalf + kPartial][j], tail[j]));
     for (int r = kHalf + kPartial + 1; r < kFull + kPartial; r++)
         for (int j = 0; j < W; j++) put(c[r][j]);
+    // K short-reduction versions of a constant c: X_j = c * 2^(256 (j+1)/K - 256), j = 0..K-1, i.e. X_{K-1} = c
+    // and each step down multiplies by 2^(-256/K) = mul(., 2^(256 - 256/K) as a plain integer).
+    auto put_versions = [&](const F& cst, int K) {
+        F down = kZero;
+        if (K == 4) down.l[3] = 1;       // 2^192
+        else if (K == 2) down.l[2] = 1;  // 2^128
+        F ver[4];
+        ver[K - 1] = cst;
+        for (int j = K - 2; j >= 0; j--) ver[j] = mul(ver[j + 1], down);
+        for (int j = 0; j < K; j++) put(ver[j]);
+    };
     for (int i = 0; i < W; i++)
-        for (int j = 0; j < W; j++) put(M[i][j]);
+        for (int j = 0; j < W; j++) put_versions(M[i][j], short_row(W));
     for (int i = 0; i < W; i++)
-        for (int j = 0; j < W; j++) put(D[i][j]);
+        for (int j = 0; j < W; j++) put_versions(D[i][j], short_row(W));
     for (int j = 0; j < W; j++) put(c4[j]);
-    const int K = short_versions(W);
-    // mul(a, 2^(256 - 256/K) as a plain integer) = a * 2^(-256/K): one step down the version ladder
-    F down = kZero;
-    if (K == 4) down.l[3] = 1;            // 2^192
-    else if (K == 2) down.l[2] = 1;       // 2^128
     for (int q = 0; q < kPartial; q++) {
         put(e[q]);
-        put(sp[q].dd);
-        for (int i = 0; i < t; i++) put(sp[q].chat[i]);
-        for (int i = 0; i < t; i++) {
-            F ver[4];
-            ver[K - 1] = sp[q].b[i];
-            for (int j = K - 2; j >= 0; j--) ver[j] = mul(ver[j + 1], down);
-            for (int j = 0; j < K; j++) put(ver[j]);
-        }
+        put_versions(sp[q].dd, short_dot(W));
+        for (int i = 0; i < t; i++) put_versions(sp[q].chat[i], short_dot(W));
+        for (int i = 0; i < t; i++) put_versions(sp[q].b[i], short_b(W));
     }
     return out.size() == table_entries(W) * 4;
 }

@@ -3,8 +3,8 @@
 // rounds.  Memory traffic is 2*32*W bytes per permutation (320 B at W=5) against ~1e5 integer
 // multiplies, so these kernels are bound by the integer-multiply pipe, not by HBM.
 #pragma once
-#ifndef HADES_W
-#error "define HADES_W before including width_impl.cuh"
+#if !defined(HADES_W) || !defined(HADES_ALGO)
+#error "define HADES_W (3|5|9) and HADES_ALGO (0 dense | 1 optimised) before including width_impl.cuh"
 #endif
 #include <string.h>
 
@@ -21,19 +21,24 @@ constexpr int kDenseEntries = kRounds * W + W * W;
 // ---- constant tables of this width (uploaded once per device by hades_init) ----------------------
 // dense: ROUND_CONSTANTS[0 .. 67W) (src/round_constants.rs:29-48) then MDS_MATRIX row-major
 //        (src/mds_matrix.rs:18-40); opt: the derived layout of host_tables.hpp.  8 u32 limbs each.
-__constant__ uint32_t c_dense[kDenseEntries * 8];
-__constant__ uint32_t c_opt[Layout::kEntries * 8];
+// One table per translation unit: the dense and the optimised kernels of a width live in separate TUs
+// (HADES_ALGO) because together their tables exceed the 64 KB constant bank.
+constexpr int kAlgo = HADES_ALGO;
+constexpr int kTableEntries = kAlgo == 0 ? kDenseEntries : Layout::kEntries;
+__constant__ uint32_t c_table[kTableEntries * 8];
+static_assert(sizeof(uint32_t) * kTableEntries * 8 + 32 <= 65536, "constant bank overflow");
 
 struct DenseConsts {
-    static __device__ __forceinline__ uint32_t ark(int idx, int k) { return c_dense[idx * 8 + k]; }
-    static __device__ __forceinline__ uint32_t mds(int r, int c, int k) { return c_dense[(kRounds * W + r * W + c) * 8 + k]; }
+    static __device__ __forceinline__ uint32_t ark(int idx, int k) { return c_table[idx * 8 + k]; }
+    static __device__ __forceinline__ uint32_t mds(int r, int c, int k) { return c_table[(kRounds * W + r * W + c) * 8 + k]; }
 };
 struct OptTab {
-    static __device__ __forceinline__ uint32_t tab(int entry, int k) { return c_opt[entry * 8 + k]; }
+    static __device__ __forceinline__ uint32_t tab(int entry, int k) { return c_table[entry * 8 + k]; }
 };
 
 template <int ALGO>
 __device__ __forceinline__ void permute(Fr (&s)[W]) {
+    static_assert(ALGO == kAlgo, "this translation unit holds one algorithm");
     if constexpr (ALGO == 0) hades_perm<W, DenseConsts>(s);
     else hades_perm_opt<W, OptTab>(s);
 }
@@ -63,6 +68,7 @@ __global__ void __launch_bounds__(kPermThreads, MINB) perm_batch_kernel(uint4* _
     for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
 }
 
+#if HADES_ALGO == 1
 // Lockstep variant: BLOCK threads per block, one barrier per round; out-of-range threads compute on the
 // last state and skip the store so that every thread reaches every barrier.
 struct BlockSync {
@@ -129,6 +135,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) perm_batch_lockstep_kernel(uint4*
     }
 }
 
+#endif  // HADES_ALGO == 1
+
 #if HADES_W == 5
 // Montgomery forms of the two small constants the compositions need (checked in tests).
 __device__ __forceinline__ void fr_set_one(Fr& x) {  // 1 * R mod p
@@ -163,6 +171,7 @@ merkle_level_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_
     fr_store(out + i * 2, s[1]);
 }
 
+#if HADES_ALGO == 1
 // Lockstep Merkle level: same launch shape as the perm kernel (one barrier per round, no early exit); a
 // warp's 32 x 128 B of children are moved with coalesced 128-bit loads through padded shared memory.
 template <int BLOCK, int MINB>
@@ -193,6 +202,7 @@ merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ o
     hades_perm_opt<5, OptTab, BlockSync>(s);
     if (live) fr_store(out + (warp_first + lane) * 2, s[1]);
 }
+#endif  // HADES_ALGO == 1
 
 // ---- sponge: rate 4 / capacity 1, one message per thread (CSR offsets) ------------------------------
 // `order` (optional) maps thread -> message so that a warp works on messages of equal block count.
@@ -232,33 +242,27 @@ sponge_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offs
 #endif  // HADES_W == 5
 
 // ---- host-side launchers ---------------------------------------------------------------------------
-cudaError_t upload(const uint64_t* dense, const uint64_t* opt) {
+cudaError_t upload(const uint64_t* table) {
     cudaError_t e = upload_modulus();
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(c_dense, dense, sizeof(c_dense), 0, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_opt, opt, sizeof(c_opt), 0, cudaMemcpyHostToDevice);
+    return cudaMemcpyToSymbol(c_table, table, sizeof(c_table), 0, cudaMemcpyHostToDevice);
 }
 
 // regs: 0 -> minBlocks 4 (<=128 registers), 1 -> 3 (<=168), 2 -> 2 (<=255), 3 -> 5 (<=96)
-#define HADES_DISPATCH(KERNEL, v, ...)                                                   \
-    do {                                                                                 \
-        const int key_ = (v).algo * 4 + (v).regs;                                        \
-        switch (key_) {                                                                  \
-            case 0: KERNEL<0, 4> __VA_ARGS__; break;                                     \
-            case 1: KERNEL<0, 3> __VA_ARGS__; break;                                     \
-            case 2: KERNEL<0, 2> __VA_ARGS__; break;                                     \
-            case 3: KERNEL<0, 5> __VA_ARGS__; break;                                     \
-            case 4: KERNEL<1, 4> __VA_ARGS__; break;                                     \
-            case 5: KERNEL<1, 3> __VA_ARGS__; break;                                     \
-            case 6: KERNEL<1, 2> __VA_ARGS__; break;                                     \
-            default: KERNEL<1, 5> __VA_ARGS__; break;                                    \
-        }                                                                                \
+#define HADES_DISPATCH(KERNEL, v, ...)                                  \
+    do {                                                                \
+        switch ((v).regs) {                                             \
+            case 0: KERNEL<kAlgo, 4> __VA_ARGS__; break;                \
+            case 1: KERNEL<kAlgo, 3> __VA_ARGS__; break;                \
+            case 2: KERNEL<kAlgo, 2> __VA_ARGS__; break;                \
+            default: KERNEL<kAlgo, 5> __VA_ARGS__; break;               \
+        }                                                               \
     } while (0)
 
 cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    if (v.algo == 1 && v.regs >= 4) {  // lockstep launches: regs 4 -> 256 threads per block, 5 -> 512, 6.. experimental
+#if HADES_ALGO == 1
+    if (v.regs >= 4) {  // lockstep launches: regs 4 -> 256 threads per block, 5 -> 512, 6.. experimental
         uint4* p = reinterpret_cast<uint4*>(d_states);
         switch (v.regs) {
             case 4: perm_batch_lockstep_kernel<256, 2><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n); break;
@@ -282,6 +286,7 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
         }
         return cudaGetLastError();
     }
+#endif
     size_t blocks = (n + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     if (v.regs >= 4) v.regs = 0;  // dense schedule has no lockstep build
@@ -292,11 +297,13 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
 #if HADES_W == 5
 cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s) {
     if (n_out == 0) return cudaSuccess;
-    if (v.algo == 1 && v.regs >= 4) {  // lockstep launch shapes share one Merkle build
+#if HADES_ALGO == 1
+    if (v.regs >= 4) {  // lockstep launch shapes share one Merkle build
         merkle_level_lockstep_kernel<128, 5><<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(
             reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out);
         return cudaGetLastError();
     }
+#endif
     if (v.regs >= 4) v.regs = 0;
     size_t blocks = (n_out + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
@@ -317,36 +324,34 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
 }
 #endif
 
-#define HADES_ATTR(KERNEL, v, out)                                                       \
-    ((v).algo * 4 + (v).regs == 0   ? cudaFuncGetAttributes(out, KERNEL<0, 4>)           \
-     : (v).algo * 4 + (v).regs == 1 ? cudaFuncGetAttributes(out, KERNEL<0, 3>)           \
-     : (v).algo * 4 + (v).regs == 2 ? cudaFuncGetAttributes(out, KERNEL<0, 2>)           \
-     : (v).algo * 4 + (v).regs == 3 ? cudaFuncGetAttributes(out, KERNEL<0, 5>)           \
-     : (v).algo * 4 + (v).regs == 4 ? cudaFuncGetAttributes(out, KERNEL<1, 4>)           \
-     : (v).algo * 4 + (v).regs == 5 ? cudaFuncGetAttributes(out, KERNEL<1, 3>)           \
-     : (v).algo * 4 + (v).regs == 6 ? cudaFuncGetAttributes(out, KERNEL<1, 2>)           \
-                                    : cudaFuncGetAttributes(out, KERNEL<1, 5>))
+#define HADES_ATTR(KERNEL, v, out)                                              \
+    ((v).regs == 0   ? cudaFuncGetAttributes(out, KERNEL<kAlgo, 4>)             \
+     : (v).regs == 1 ? cudaFuncGetAttributes(out, KERNEL<kAlgo, 3>)             \
+     : (v).regs == 2 ? cudaFuncGetAttributes(out, KERNEL<kAlgo, 2>)             \
+                     : cudaFuncGetAttributes(out, KERNEL<kAlgo, 5>))
 
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 5) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<512, 1>);
+#if HADES_ALGO == 1
+    if (!strcmp(kernel, "perm") && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);
+    if (!strcmp(kernel, "perm") && v.regs == 5) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<512, 1>);
 #if HADES_W == 9
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 2>);
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 3>);
+    if (!strcmp(kernel, "perm") && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 2>);
+    if (!strcmp(kernel, "perm") && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 3>);
 #endif
 #if HADES_W == 3
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 7>);
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 5>);
+    if (!strcmp(kernel, "perm") && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 7>);
+    if (!strcmp(kernel, "perm") && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 5>);
 #endif
 #if HADES_W == 5
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 5>);
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<384, 1>);
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 8) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<640, 1>);
-    if (!strcmp(kernel, "perm") && v.algo == 1 && v.regs == 9) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 4>);
+    if (!strcmp(kernel, "perm") && v.regs == 6) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 5>);
+    if (!strcmp(kernel, "perm") && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<384, 1>);
+    if (!strcmp(kernel, "perm") && v.regs == 8) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<640, 1>);
+    if (!strcmp(kernel, "perm") && v.regs == 9) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 4>);
 #endif
 #if HADES_W == 5
-    if (!strcmp(kernel, "merkle") && v.algo == 1 && v.regs >= 4) return cudaFuncGetAttributes(out, merkle_level_lockstep_kernel<128, 5>);
+    if (!strcmp(kernel, "merkle") && v.regs >= 4) return cudaFuncGetAttributes(out, merkle_level_lockstep_kernel<128, 5>);
 #endif
+#endif  // HADES_ALGO == 1
     if (v.regs >= 4) v.regs = 0;  // sponge / dense: plain 128-thread launches
     if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);
 #if HADES_W == 5
@@ -356,7 +361,7 @@ cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* o
     return cudaErrorInvalidValue;
 }
 
-const WidthOps kOps = {W, (size_t)kDenseEntries * 4, (size_t)Layout::kEntries * 4, upload, launch_perm,
+const WidthOps kOps = {W, kAlgo, (size_t)kTableEntries * 4, upload, launch_perm,
 #if HADES_W == 5
                        launch_merkle_level, launch_sponge,
 #else

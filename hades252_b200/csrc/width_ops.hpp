@@ -1,6 +1,6 @@
 // Interface between the engine (C ABI, hades_engine.cu) and the per-width kernel translation units
-// (hades_w3.cu / hades_w5.cu / hades_w9.cu).  Each width is its own TU because every TU owns a
-// separate 64 KB `__constant__` bank: the width-9 tables alone need 61 KB.
+// (hades_w{3,5,9}.cu, hades_w{3,5,9}_dense.cu).  Each (width, algorithm) is its own TU because every
+// TU owns a separate 64 KB `__constant__` bank and the optimised tables alone need up to 62 KB.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -24,9 +24,9 @@ constexpr int kPermThreads = 128;
 
 struct WidthOps {
     int width;
-    size_t dense_u64;  // (67*W + W*W) * 4
-    size_t opt_u64;    // OptLayout<W>::kEntries * 4
-    cudaError_t (*upload)(const uint64_t* dense, const uint64_t* opt);  // to the CURRENT device
+    int algo;          // 0: dense table (67*W + W*W entries); 1: optimised table (OptLayout<W>::kEntries)
+    size_t table_u64;  // entries * 4
+    cudaError_t (*upload)(const uint64_t* table);  // to the CURRENT device
     cudaError_t (*launch_perm)(Variant v, uint64_t* d_states, size_t n, cudaStream_t s);
     // width 5 only (nullptr otherwise)
     cudaError_t (*launch_merkle_level)(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s);
@@ -35,8 +35,9 @@ struct WidthOps {
     cudaError_t (*func_attributes)(const char* kernel, Variant v, cudaFuncAttributes* out);
 };
 
-const WidthOps* width_ops_3();
-const WidthOps* width_ops_5();
-const WidthOps* width_ops_9();
+// one translation unit per (width, algo): hades_w{3,5,9}.cu (optimised) and hades_w{3,5,9}_dense.cu
+const WidthOps* width_ops_3(int algo);
+const WidthOps* width_ops_5(int algo);
+const WidthOps* width_ops_9(int algo);
 
 }  // namespace hades
