@@ -37,8 +37,9 @@ sys.path.insert(0, ROOT)
 WIDTH = 5
 LIMB_PRODUCTS_PER_PERM = 268192   # 1972 Fr mul x 136 (8-limb CIOS), SURVEY.md 8(d)
 # IMAD.WIDE products the default kernel actually executes per perm:
-#   partial round 2*(36+48) + (64+48) + (5*64+48) + 4*(64+48) = 1096, x59; full round 5*280 + 5*368 = 3240, x8
-EXECUTED_PRODUCTS_PER_PERM = 59 * 1096 + 8 * 3240
+#   partial round: x^5 2*(36+48) + (64+48) = 280; 5-term dot 5*64+48 = 368; 4 short-reduced b products 4*(64+12) = 304
+#   -> 952, x59; full round 5*280 + 5*368 = 3240, x8
+EXECUTED_PRODUCTS_PER_PERM = 59 * 952 + 8 * 3240
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE default-kernel launch over 2^26 states, from the
 # `ncu --set full` capture summarised in profiles/r01_ncu_perm5_2p26_default.txt (10.846 + 10.707 GB)
 NCU_TRAFFIC_BYTES_2P26 = 21_552_500_000
