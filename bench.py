@@ -570,6 +570,11 @@ def emit(obj):
 
 def main():
     args = parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched bare: re-exec under torchrun, one rank per GPU (the driver already launches it this way)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+                                   os.path.abspath(__file__), *sys.argv[1:]])
     _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)

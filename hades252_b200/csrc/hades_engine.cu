@@ -377,26 +377,27 @@ int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elem
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     // Length bucketing: sort message indices by permutation count so that the 32 messages of a warp
     // need the same number of perms (a strictly sequential chain per message).
-    uint32_t *keys = nullptr, *keys_out = nullptr, *idx = nullptr, *order = nullptr;
-    void* tmp = nullptr;
+    struct AsyncBufs {  // stream-ordered temporaries, released on every exit path
+        cudaStream_t st;
+        void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        explicit AsyncBufs(cudaStream_t s) : st(s) {}
+        ~AsyncBufs() { for (void* q : p) if (q) cudaFreeAsync(q, st); }
+    } bufs(st);
     size_t tmp_bytes = 0;
     const int n = (int)n_msgs;
-    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
-    CUDA_TRY(ctx, cudaMallocAsync(&keys, n_msgs * 4, st));
-    CUDA_TRY(ctx, cudaMallocAsync(&keys_out, n_msgs * 4, st));
-    CUDA_TRY(ctx, cudaMallocAsync(&idx, n_msgs * 4, st));
-    CUDA_TRY(ctx, cudaMallocAsync(&order, n_msgs * 4, st));
-    CUDA_TRY(ctx, cudaMallocAsync(&tmp, tmp_bytes, st));
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                  (uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 32, st));
+    for (int i = 0; i < 4; i++) CUDA_TRY(ctx, cudaMallocAsync(&bufs.p[i], n_msgs * 4, st));
+    CUDA_TRY(ctx, cudaMallocAsync(&bufs.p[4], tmp_bytes, st));
+    uint32_t *keys = (uint32_t*)bufs.p[0], *keys_out = (uint32_t*)bufs.p[1], *idx = (uint32_t*)bufs.p[2],
+             *order = (uint32_t*)bufs.p[3];
     sponge_keys_kernel<<<(unsigned)std::min<size_t>((n_msgs + 255) / 256, 148 * 16), 256, 0, st>>>(d_offsets, keys, idx, n_msgs);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(bufs.p[4], tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
     ctx->launches++;
-    int rc = HADES_OK;
-    cudaError_t e = ctx->ops()->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, st);
-    if (e != cudaSuccess) rc = fail(ctx, HADES_ERR_CUDA, "sponge launch failed: %s", cudaGetErrorString(e));
-    cudaFreeAsync(keys, st); cudaFreeAsync(keys_out, st); cudaFreeAsync(idx, st); cudaFreeAsync(order, st); cudaFreeAsync(tmp, st);
-    return rc;
+    CUDA_TRY(ctx, ctx->ops()->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, st));
+    return HADES_OK;
 }
 
 int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs, uint64_t* out) {
