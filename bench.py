@@ -262,7 +262,18 @@ def run_ours(args):
     value = world * n * args.steps / (total_ms * 1e-3)
     kernel_ms = statistics.mean(step_ms)
 
-    # correctness spot check (outside the timed region): digest of the final states + a sample
+    # correctness check at full size (outside the timed region): a strided 2^12-state sample of the final
+    # states against the CPU oracle applied (warmup + steps) times to the regenerated inputs, plus a digest
+    verified = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_oracle
+        k = min(n, 1 << 12)
+        idx = torch.arange(0, n, n // k, device="cuda")[:k]
+        got = states.view(n, WIDTH * 4)[idx].cpu().numpy().view(np.uint64).reshape(k, WIDTH, 4)
+        want = np.stack([cpu_oracle.gen_elems((rank * n + int(i)) * WIDTH, WIDTH, SEED) for i in idx.cpu().numpy()])
+        for _ in range(args.warmup + args.steps):
+            want = cpu_oracle.perm_batch(want, WIDTH)
+        verified = bool(np.array_equal(got, want))
     dig = torch.zeros(4, dtype=torch.int64, device="cuda")
     strat.digest_device(states.data_ptr(), 0, n * WIDTH * 4, dig.data_ptr(), sptr)
     torch.cuda.synchronize()
@@ -346,6 +357,7 @@ def run_ours(args):
             "roofline_hbm": {"achieved_gbs": per_gpu * HBM_BYTES_PER_PERM / 1e9, "peak_gbs": pk.get("hbm_gbs"),
                              "peak_source": pk_src, "frac": per_gpu * HBM_BYTES_PER_PERM / 1e9 / pk.get("hbm_gbs", 1)},
             "kernel_info": info, "gpu_launches": launches, "clocks": clocks, "digest": digest,
+            "oracle_sample_match": verified,
             "e2e": e2e, "cpu_baseline": cpu_baseline,
         }
         emit(out)
