@@ -34,6 +34,7 @@ struct DenseConsts {
 };
 struct OptTab {
     static __device__ __forceinline__ uint32_t tab(int entry, int k) { return c_table[entry * 8 + k]; }
+    static __device__ __forceinline__ const uint32_t* ptr(int entry) { return c_table + entry * 8; }
 };
 
 template <int ALGO>

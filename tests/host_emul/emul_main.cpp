@@ -26,6 +26,7 @@ static std::vector<uint64_t> g_opt[10];
 template <int W>
 struct HostTab {
     static uint32_t tab(int entry, int k) { return (uint32_t)(g_opt[W][(size_t)entry * 4 + k / 2] >> (32 * (k & 1))); }
+    static const uint32_t* ptr(int entry) { return reinterpret_cast<const uint32_t*>(g_opt[W].data()) + (size_t)entry * 8; }
 };
 
 static uint64_t rng_state = 0x1234567;
