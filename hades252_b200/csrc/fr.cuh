@@ -714,10 +714,18 @@ HADES_DEV void fr_sqr_lazy(Fr& out, const Fr& a) {
     for (int k = 0; k < 8; k++) out.l[k] = r[k];
 }
 
+// x^4 by two trips through ONE squaring body (a real loop: the kernels are instruction-cache sensitive)
+HADES_DEV void fr_pow4_lazy(Fr& x4, const Fr& x) {
+    x4 = x;
+#if !HADES_EMUL
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 2; i++) fr_sqr_lazy(x4, x4);
+}
+
 HADES_DEV void fr_sbox(Fr& x) {
-    Fr x2, x4;
-    fr_sqr_lazy(x2, x);
-    fr_sqr_lazy(x4, x2);
+    Fr x4;
+    fr_pow4_lazy(x4, x);
     fr_mul(x, x4, x);
 }
 

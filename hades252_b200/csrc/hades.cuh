@@ -195,9 +195,8 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
         for (int k = 0; k < 8; k++) e.l[k] = T::tab(base, k);
         fr_add(s[t], s[t], e);
     }
-    Fr y, x2, x4;
-    fr_sqr_lazy(x2, s[t]);
-    fr_sqr_lazy(x4, x2);
+    Fr y, x4;
+    fr_pow4_lazy(x4, s[t]);
     fr_mul_lazy(y, x4, s[t]);
     // new last word = sum_{j<t} chat_j * w_j + d * y  (uses the OLD w_j)
     // bound: (t + 1.886) p^2  =>  < p (1 + 0.4528 (t + 1.886)): W=5 -> 3.67p, W=9 -> 5.48p
