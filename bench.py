@@ -388,6 +388,8 @@ def run_merkle(args):
     torch, dist, world, rank, local = _dist_setup()
     from hades252_b200 import CudaStrategy, sharding
     strat = CudaStrategy([local])
+    if args.variant:
+        strat.set_variant(*(int(x) for x in args.variant.split(",")))
     n = 1 << args.log2_leaves
     plan = sharding.merkle_plan(n, world)
     lo, hi = sharding.shard_range(n, rank, world)
@@ -457,6 +459,8 @@ def run_sponge(args):
     torch, dist, world, rank, local = _dist_setup()
     from hades252_b200 import CudaStrategy, sharding
     strat = CudaStrategy([local])
+    if args.variant:
+        strat.set_variant(*(int(x) for x in args.variant.split(",")))
     n = 1 << args.log2_msgs
     seed2 = SEED ^ 0x5A5A5A5A
     idx = np.arange(n, dtype=np.uint64)

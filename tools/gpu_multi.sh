@@ -7,8 +7,8 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err || tail -5 gpurun_out/bench_n$N.err
 python -c "
 import json; d=json.load(open('gpurun_out/bench_n$N.json')); print('perm N=$N', '%.4g' % d['value'], 'e2e %.4g' % d['e2e']['value'], d['clocks'])"
-timeout 600 $TR bench.py --gpus $N --workload merkle --steps 3 --warmup 1 > gpurun_out/bench_merkle_n$N.json 2>> gpurun_out/bench_n$N.err || tail -5 gpurun_out/bench_n$N.err
+timeout 600 $TR bench.py --gpus $N --workload merkle --steps 5 --warmup 3 > gpurun_out/bench_merkle_n$N.json 2>> gpurun_out/bench_n$N.err || tail -5 gpurun_out/bench_n$N.err
 cat gpurun_out/bench_merkle_n$N.json
-timeout 600 $TR bench.py --gpus $N --workload sponge --steps 3 --warmup 1 > gpurun_out/bench_sponge_n$N.json 2>> gpurun_out/bench_n$N.err || tail -5 gpurun_out/bench_n$N.err
+timeout 600 $TR bench.py --gpus $N --workload sponge --steps 5 --warmup 3 > gpurun_out/bench_sponge_n$N.json 2>> gpurun_out/bench_n$N.err || tail -5 gpurun_out/bench_n$N.err
 cut -c1-400 gpurun_out/bench_sponge_n$N.json
 timeout 300 $TR bench.py --gpus $N --impl reference --steps 1 --warmup 1 | cut -c1-200
