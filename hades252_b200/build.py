@@ -32,10 +32,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "lib", "obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("HADES_NVCC_EXTRA", "").split()  # e.g. -DHADES_SYNC_MID for experiments
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", "-o", obj, os.path.join(CSRC, src)]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return src, obj, cmd, res
 

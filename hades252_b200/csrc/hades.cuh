@@ -138,6 +138,10 @@ HADES_DEV void add_table_vector(Fr (&s)[W], int base) {
 #define HADES_NO_UNROLL _Pragma("unroll 1")
 #endif
 
+struct NoSync {
+    static HADES_DEV void sync() {}
+};
+
 template <int N>
 HADES_DEV void rotate_in(Fr (&s)[N], const Fr& incoming) {  // s <- (s[1], ..., s[N-1], incoming)
     Fr tmp = incoming;
@@ -184,7 +188,7 @@ HADES_DEV void full_round_opt(Fr (&s)[W], int ark, int mat) {
 }
 
 // one sparse partial round; `base` = table entry of {e, d, b[W-1], chat[W-1]}
-template <int W, class T>
+template <int W, class T, class Sync = NoSync>
 HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
     constexpr int t = W - 1;
     // last word: + e_q, then x^5.  The S-box output stays lazily reduced (< 1.886p < 2^256): it only
@@ -198,6 +202,9 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
     Fr y, x4;
     fr_pow4_lazy(x4, s[t]);
     fr_mul_lazy(y, x4, s[t]);
+#ifdef HADES_SYNC_MID
+    Sync::sync();
+#endif
     // new last word = sum_{j<t} chat_j * w_j + d * y  (uses the OLD w_j)
     // bound: (t + 1.886) p^2  =>  < p (1 + 0.4528 (t + 1.886)): W=5 -> 3.67p, W=9 -> 5.48p
     {
@@ -243,10 +250,6 @@ HADES_DEV void partial_round_opt(Fr (&s)[W], int base) {
     for (int i = 0; i < t; i++) s[i] = w[i];
 }
 
-struct NoSync {
-    static HADES_DEV void sync() {}
-};
-
 // `Sync::sync()` is called once per round; kernels with uniform control flow pass a block barrier so
 // that the warps of a block stay in lockstep and share instruction-cache lines.
 template <int W, class T, class Sync = NoSync>
@@ -265,7 +268,7 @@ HADES_DEV void hades_perm_opt(Fr (&s)[W]) {
 #pragma unroll 1
 #endif
             for (int q = 0; q < kPartialRounds; q++) {
-                partial_round_opt<W, T>(s, L::kSparse + q * L::kSparseStride);
+                partial_round_opt<W, T, Sync>(s, L::kSparse + q * L::kSparseStride);
                 Sync::sync();
             }
         }
