@@ -374,3 +374,25 @@ def test_permutation_is_a_bijection_on_a_sample(cuda_strategy, oracle):
     o = s.copy()
     cuda_strategy.perm_batch(o)
     assert len({bytes(x) for x in o.reshape(n, -1)}) == n
+
+
+def test_single_process_multi_device_context(oracle):
+    """`CudaStrategy::new(&[0, 1, ...])`: one context over every GPU of the box; host batches, Merkle
+    leaves and sponge messages are sharded inside the C library (skipped on a 1-GPU box)."""
+    import torch
+    from hades252_b200 import CudaStrategy
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 300001
+    s = oracle.gen_elems(11, 5 * n).reshape(n, 5, 4)
+    with CudaStrategy(list(range(g))) as strat:
+        got = s.copy()
+        strat.perm_batch(got)
+        assert np.array_equal(got, oracle.perm_batch(s))
+        leaves = oracle.gen_elems(12, 4 ** 8)
+        assert np.array_equal(strat.merkle_root(leaves), oracle.merkle_root(leaves))
+        lens = np.random.default_rng(2).integers(0, 33, size=60000)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        elems = oracle.gen_elems(13, int(offsets[-1]))
+        assert np.array_equal(strat.sponge_batch(elems, offsets), oracle.sponge_batch(elems, offsets))
