@@ -31,6 +31,7 @@ constexpr size_t kChunkBytes = (size_t)96 << 20;  // target bytes per pipeline c
 
 struct DeviceState {
     int ordinal = 0;
+    uint64_t* generic_tables = nullptr;  // widths without a tuned kernel: ark ++ mds in global memory
     cudaStream_t streams[kNumBuf] = {nullptr, nullptr, nullptr};
     uint64_t* chunk[kNumBuf] = {nullptr, nullptr, nullptr};
     size_t chunk_bytes = 0;
@@ -44,6 +45,7 @@ struct hades_ctx {
     uint32_t width = 0;
     const WidthOps* ops2[2] = {nullptr, nullptr};  // [algo]
     const WidthOps* ops() const { return ops2[variant.algo]; }
+    bool generic() const { return ops2[0] == nullptr; }  // no tuned kernel for this width
     Variant variant = {1, 0};  // optimised schedule, <=128 registers
     std::vector<DeviceState> devs;
     mutable std::string err;
@@ -94,9 +96,14 @@ int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dens
     return HADES_OK;
 }
 
-int launch_perm_w(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t stream) {
+int launch_perm_w(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t stream, const DeviceState* dev = nullptr) {
     if (n == 0) return HADES_OK;
     ctx->launches++;
+    if (ctx->generic()) {
+        if (!dev) return fail(ctx, HADES_ERR_INVALID_ARG, "internal: generic launch without a device");
+        CUDA_TRY(ctx, generic_launch_perm(d_states, n, (int)ctx->width, dev->generic_tables, stream));
+        return HADES_OK;
+    }
     CUDA_TRY(ctx, ctx->ops()->launch_perm(ctx->variant, d_states, n, stream));
     return HADES_OK;
 }
@@ -146,8 +153,9 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     if (!out || !ark_limbs || !mds_limbs || n_dev < 1)
         return fail(nullptr, HADES_ERR_INVALID_ARG, "hades_init: null pointer or n_dev < 1");
     *out = nullptr;
-    if (width != 3 && width != 5 && width != 9)
-        return fail(nullptr, HADES_ERR_INVALID_ARG, "hades_init: width %u not built (kernels exist for 3, 5, 9)", width);
+    if (width < 2 || width > 14)
+        return fail(nullptr, HADES_ERR_INVALID_ARG, "hades_init: width %u out of range (2..14; 67*width round constants must fit 960)", width);
+    const bool tuned = width == 3 || width == 5 || width == 9;
     if ((size_t)kRounds * width > n_ark)
         return fail(nullptr, HADES_ERR_OUT_OF_CONSTANTS, "Hades252 out of ARK constants: need %zu, got %zu",
                     (size_t)kRounds * width, n_ark);
@@ -158,15 +166,18 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
-    for (int a = 0; a < 2; a++) ctx->ops2[a] = width == 3 ? width_ops_3(a) : width == 5 ? width_ops_5(a) : width_ops_9(a);
+    if (tuned)
+        for (int a = 0; a < 2; a++) ctx->ops2[a] = width == 3 ? width_ops_3(a) : width == 5 ? width_ops_5(a) : width_ops_9(a);
     ctx->variant = Variant{1, width == 9 ? 7 : 6};  // lockstep 128-thread blocks: x7 (W=3), x5 (W=5), x3 (W=9) per SM
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
     std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
     int rc = HADES_OK;
-    if (dense.size() != ctx->ops2[0]->table_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
-    if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops2[1]->table_u64))
-        rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the sparse partial-round tables (singular MDS sub-matrix)");
+    if (tuned) {
+        if (dense.size() != ctx->ops2[0]->table_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
+        if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops2[1]->table_u64))
+            rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the sparse partial-round tables (singular MDS sub-matrix)");
+    }
     for (int g = 0; g < n_dev && rc == HADES_OK; g++) {
         DeviceState d;
         d.ordinal = devices ? devices[g] : g;
@@ -181,6 +192,12 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
         auto step = [&]() -> int {
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
             for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d.streams[b], cudaStreamNonBlocking));
+            if (!tuned) {  // generic kernel: per-context tables in global memory
+                CUDA_TRY(ctx, generic_upload_modulus());
+                CUDA_TRY(ctx, cudaMalloc(&d.generic_tables, dense.size() * 8));
+                CUDA_TRY(ctx, cudaMemcpy(d.generic_tables, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice));
+                return HADES_OK;
+            }
             return upload_tables(ctx, d.ordinal, dense, opt);
         };
         rc = step();
@@ -203,6 +220,7 @@ void hades_destroy(hades_ctx* ctx) {
             if (d.chunk[b]) cudaFree(d.chunk[b]);
             if (d.streams[b]) cudaStreamDestroy(d.streams[b]);
         }
+        if (d.generic_tables) cudaFree(d.generic_tables);
     }
     delete ctx;
 }
@@ -217,7 +235,7 @@ int hades_perm_batch_dev(hades_ctx* ctx, int dev_index, uint64_t* d_states, size
     if (n == 0) return HADES_OK;
     if (!d_states || ((uintptr_t)d_states & 15)) return fail(ctx, HADES_ERR_INVALID_ARG, "d_states must be non-null and 16-byte aligned");
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
-    return launch_perm_w(ctx, d_states, n, (cudaStream_t)stream);
+    return launch_perm_w(ctx, d_states, n, (cudaStream_t)stream, &ctx->devs[dev_index]);
 }
 
 int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
@@ -255,7 +273,7 @@ int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
             auto step = [&]() -> int {
                 CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
                 CUDA_TRY(ctx, cudaMemcpyAsync(d.chunk[b], h, cnt * state_bytes, cudaMemcpyHostToDevice, d.streams[b]));
-                int r = launch_perm_w(ctx, d.chunk[b], cnt, d.streams[b]);
+                int r = launch_perm_w(ctx, d.chunk[b], cnt, d.streams[b], &d);
                 if (r) return r;
                 CUDA_TRY(ctx, cudaMemcpyAsync(h, d.chunk[b], cnt * state_bytes, cudaMemcpyDeviceToHost, d.streams[b]));
                 return HADES_OK;
@@ -540,7 +558,8 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
     if (!ctx || !kernel) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
     cudaFuncAttributes a;
-    cudaError_t e = ctx->ops()->func_attributes(kernel, ctx->variant, &a);
+    cudaError_t e = ctx->generic() ? (strcmp(kernel, "perm") ? cudaErrorInvalidValue : generic_func_attributes(&a))
+                                   : ctx->ops()->func_attributes(kernel, ctx->variant, &a);
     if (e == cudaErrorInvalidValue) return fail(ctx, HADES_ERR_INVALID_ARG, "unknown kernel '%s' for width %u", kernel, ctx->width);
     CUDA_TRY(ctx, e);
     if (regs_per_thread) *regs_per_thread = a.numRegs;
@@ -551,6 +570,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
 
 int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
     if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 10) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
+    if (ctx->generic()) return fail(ctx, HADES_ERR_INVALID_ARG, "width %u runs the generic kernel, which has no variants", ctx->width);
     ctx->variant = Variant{algo, regs};
     return HADES_OK;
 }

@@ -40,4 +40,9 @@ const WidthOps* width_ops_3(int algo);
 const WidthOps* width_ops_5(int algo);
 const WidthOps* width_ops_9(int algo);
 
+// generic-width kernel (hades_generic.cu): any width in 2..14, dense schedule, tables in global memory
+cudaError_t generic_upload_modulus();  // to the CURRENT device
+cudaError_t generic_launch_perm(uint64_t* d_states, size_t n, int width, const uint64_t* d_tables, cudaStream_t s);
+cudaError_t generic_func_attributes(cudaFuncAttributes* out);
+
 }  // namespace hades

@@ -59,7 +59,7 @@ class CudaStrategy(Strategy):
         devs = list(devices) if devices is not None else [0]
         arr = (ctypes.c_int * len(devs))(*devs)
         ark = np.ascontiguousarray(constants.round_constants())
-        mds = np.ascontiguousarray(constants.mds_matrix(self.width)) if self.width in (3, 5, 9) else np.zeros((1, 4), np.uint64)
+        mds = np.ascontiguousarray(constants.mds_matrix(self.width)) if 2 <= self.width <= 14 else np.zeros((1, 4), np.uint64)
         rc = self._lib.hades_init(ctypes.byref(self._ctx), arr, len(devs), self.width,
                                   ark.ctypes.data_as(_native.u64p), ark.shape[0], mds.ctypes.data_as(_native.u64p))
         if rc:

@@ -51,7 +51,9 @@ typedef struct hades_ctx hades_ctx;
 /*
  * Create a context over `n_dev` CUDA devices (ordinals in `devices`; NULL => device 0 only when
  * n_dev == 1, or devices 0..n_dev-1) and upload the constant tables once.
- *   width      permutation width; kernels exist for 3, 5 (the reference's WIDTH, lib.rs:27) and 9.
+ *   width      permutation width, 2..14 (67*width round constants must fit the 960 of the reference).  Tuned
+ *              kernels exist for 3, 5 (the reference's WIDTH, lib.rs:27) and 9; other widths run a generic,
+ *              slower kernel with the reference's round structure.
  *   ark_limbs  n_ark*4 u64: the raw limbs of `ROUND_CONSTANTS` (src/round_constants.rs:29-48), i.e.
  *              AFTER `BlsScalar::from_raw`.  Round r uses entries [r*width, r*width+width).
  *   mds_limbs  width*width*4 u64: raw limbs of `MDS_MATRIX` row-major (src/mds_matrix.rs:18-40).

@@ -46,8 +46,9 @@ def test_init_argument_errors(lib):
     ark = np.ascontiguousarray(constants.round_constants())
     mds = np.ascontiguousarray(constants.mds_matrix(5))
     a, m = ark.ctypes.data_as(_native.u64p), mds.ctypes.data_as(_native.u64p)
-    assert lib.hades_init(ctypes.byref(ctx), None, 1, 4, a, 960, m) == 1          # width not built
+    assert lib.hades_init(ctypes.byref(ctx), None, 1, 15, a, 960, m) == 1         # width out of range (2..14)
     assert b"width" in lib.hades_last_error(None)
+    assert lib.hades_init(ctypes.byref(ctx), None, 1, 1, a, 960, m) == 1
     assert lib.hades_init(ctypes.byref(ctx), None, 1, 5, a, 100, m) == 6          # out of ARK constants
     assert b"out of ARK constants" in lib.hades_last_error(None)
     assert lib.hades_init(ctypes.byref(ctx), None, 0, 5, a, 960, m) == 1

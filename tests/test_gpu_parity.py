@@ -159,7 +159,9 @@ def test_other_widths(oracle, w):
 def test_unsupported_width_fails_loudly():
     from hades252_b200 import CudaStrategy, HadesError
     with pytest.raises(HadesError):
-        CudaStrategy([0], width=4)
+        CudaStrategy([0], width=15)   # 67 * 15 > 960 round constants
+    with pytest.raises(HadesError):
+        CudaStrategy([0], width=1)
     with pytest.raises(HadesError):
         CudaStrategy([99])
 
@@ -396,3 +398,24 @@ def test_single_process_multi_device_context(oracle):
         offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
         elems = oracle.gen_elems(13, int(offsets[-1]))
         assert np.array_equal(strat.sponge_batch(elems, offsets), oracle.sponge_batch(elems, offsets))
+
+
+@pytest.mark.parametrize("w", [2, 4, 6, 7, 8, 10, 14])
+def test_generic_width_kernel(oracle, w):
+    """Widths without a tuned kernel (the reference allows any WIDTH with 67*WIDTH <= 960, README.md:30-31)
+    run the generic kernel; assets regenerated per assets/HOWTO.md."""
+    from hades252_b200 import CudaStrategy, HadesError
+    n = 700
+    s = oracle.gen_elems(w * 100, w * n).reshape(n, w, 4)
+    with CudaStrategy([0], width=w) as strat:
+        got = s.copy()
+        strat.perm_batch(got)
+        assert np.array_equal(got, oracle.perm_batch(s, w))
+        one = s[:1].copy()
+        strat.perm(one[0])
+        assert np.array_equal(one[0], got[0])
+        with pytest.raises(HadesError):
+            strat.merkle_root(np.zeros((4, 4), dtype=np.uint64))   # compositions are width-5 only
+        with pytest.raises(HadesError):
+            strat.set_variant(0, 0)
+        assert strat.kernel_info("perm")["regs_per_thread"] > 0
