@@ -52,3 +52,37 @@ def test_cpp_mirror_on_gpu(tmp_path, golden):
     exe = _build(tmp_path)
     res = subprocess.run([exe, *_args(golden)], capture_output=True, text=True)
     assert res.returncode == 0 and "cpp strategy OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_c_example_builds(tmp_path):
+    """examples/perm_batch.c compiles and links against the C ABI with a plain C compiler."""
+    from hades252_b200 import build
+    build.build()
+    exe = str(tmp_path / "perm_batch")
+    subprocess.check_call(["gcc", "-std=c11", "-O1", "-o", exe, os.path.join(ROOT, "examples", "perm_batch.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + LIBDIR, "-lhades_b200", "-Wl,-rpath," + LIBDIR])
+    import torch
+    res = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        # known answer: SURVEY.md 8(c), Montgomery limbs of perm([1;5])[0]
+        assert res.returncode == 0 and "935feb66a5e6cf3c 2409c7dd1a61ab1c 832c33cbf2dd481f 23338e018f505a2a" in res.stdout, res.stdout
+    else:
+        assert res.returncode == 4 and "no CPU fallback" in res.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_on_gpu(tmp_path):
+    test_c_example_builds(tmp_path)
+
+
+def test_scalar_helpers_round_trip():
+    from hades252_b200 import scalar
+    from oracle import hades_ref as H
+    for v in (0, 1, 17, 5000, H.P - 1, H.P + 5, 1 << 255):
+        limbs = scalar.from_int(v)
+        assert [int(x) for x in limbs] == H.to_mont_limbs(v % H.P)
+        assert scalar.to_int(limbs) == v % H.P
+    st = scalar.state_from_ints([1, 2, 3, 4, 5])
+    assert st.shape == (5, 4) and scalar.state_to_ints(st) == [1, 2, 3, 4, 5]
+    with pytest.raises(ValueError):
+        scalar.to_int(np.array([2**64 - 1] * 4, dtype=np.uint64))
