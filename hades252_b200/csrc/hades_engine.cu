@@ -245,10 +245,18 @@ int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
     const size_t state_bytes = (size_t)ctx->width * 32;
     const size_t G = ctx->devs.size();
     size_t chunk_states = std::max<size_t>(kPermThreads, kChunkBytes / state_bytes / kPermThreads * kPermThreads);
-    // small batches: split so that all three stages still overlap
+    // Medium batches: split into kNumBuf chunks so that H2D, kernel and D2H still overlap.  Small batches
+    // (under kMinSplitBytes per chunk) go as ONE chunk: a kernel launch is one ~340 us wave regardless of its
+    // size up to ~16k states, and with pageable host memory the copies are synchronous, so splitting would
+    // only serialise several such waves.
+    constexpr size_t kMinSplitBytes = (size_t)8 << 20;
     size_t per_dev = (n + G - 1) / G;
-    if (per_dev < chunk_states * kNumBuf)
-        chunk_states = std::max<size_t>(kPermThreads, (per_dev / kNumBuf + kPermThreads) / kPermThreads * kPermThreads);
+    if (per_dev < chunk_states * kNumBuf) {
+        if (per_dev * state_bytes >= kMinSplitBytes * kNumBuf)
+            chunk_states = std::max<size_t>(kPermThreads, (per_dev / kNumBuf + kPermThreads) / kPermThreads * kPermThreads);
+        else
+            chunk_states = std::max<size_t>(kPermThreads, (per_dev + kPermThreads - 1) / kPermThreads * kPermThreads);
+    }
     std::vector<size_t> lo(G), hi(G), next(G);
     size_t max_chunks = 0;
     for (size_t g = 0; g < G; g++) {
