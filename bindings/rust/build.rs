@@ -12,7 +12,7 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let units = [
         "hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu", "hades_w3_dense.cu", "hades_w5_dense.cu",
-        "hades_w9_dense.cu", "hades_generic.cu",
+        "hades_w9_dense.cu", "hades_w3_ccf.cu", "hades_w5_ccf.cu", "hades_w9_ccf.cu", "hades_generic.cu",
     ];
     let mut objs = Vec::new();
     for u in units {

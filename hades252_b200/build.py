@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libhades_b200.so")
 SOURCES = ["hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu",
-           "hades_w3_dense.cu", "hades_w5_dense.cu", "hades_w9_dense.cu", "hades_generic.cu"]
+           "hades_w3_dense.cu", "hades_w5_dense.cu", "hades_w9_dense.cu",
+           "hades_w3_ccf.cu", "hades_w5_ccf.cu", "hades_w9_ccf.cu", "hades_generic.cu"]
 HEADERS = ["fr.cuh", "hades.cuh", "width_impl.cuh", "width_ops.hpp", "util_kernels.cuh", "host_tables.hpp",
            os.path.join("..", "..", "include", "hades_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -275,4 +275,109 @@ HADES_DEV void hades_perm_opt(Fr (&s)[W]) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Canonical-form schedule (algo 2; derivation in host_tables.hpp, derive_tables_ccf): per partial round
+//   x += e_q ; s = x^5 ; w~_t' = alpha . w~ + s ; x' = c~ . w~ + d s ; w~_i' = w~_{i+1}
+// Same multiplications as the sparse schedule, two reductions instead of W, no per-word loop.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+struct CcfLayout {
+    static constexpr int t = W - 1;
+    static constexpr int kArk = 0;
+    static constexpr int kMds = kFullRounds * W;
+    static constexpr int kPre = kMds + W * W;
+    static constexpr int kC4 = kPre + W * W;
+    static constexpr int kE = kC4 + W;
+    static constexpr int kAlpha = kE + kPartialRounds;
+    static constexpr int kCrow = kAlpha + t;
+    static constexpr int kD = kCrow + t;
+    static constexpr int kPinv = kD + 1;
+    static constexpr int kEntries = kPinv + t * t;
+    // the full rounds reuse full_round_opt, which expects OptLayout's kShortRow == 1 layout of dense matrices
+};
+
+template <int W, class T>
+HADES_DEV void partial_round_ccf(Fr (&s)[W], int q) {
+    typedef CcfLayout<W> L;
+    constexpr int t = W - 1;
+    {
+        Fr e;
+#pragma unroll
+        for (int k = 0; k < 8; k++) e.l[k] = T::tab(L::kE + q, k);
+        fr_add(s[t], s[t], e);
+    }
+    Fr y, x4;
+    fr_pow4_lazy(x4, s[t]);
+    fr_mul_lazy(y, x4, s[t]);  // < 1.886p
+    // x' = c~ . w~ + d y   (bounds as in the sparse schedule)
+    Fr newx;
+    {
+        uint32_t r[9];
+        dot_mont<W>(
+            r, [&](int j, int k) { return j < t ? T::tab(L::kCrow + j, k) : T::tab(L::kD, k); },
+            [&](int j, int i) { return j < t ? s[j].l[i] : y.l[i]; });
+        canon<(W <= 5) ? 1 : 2>(newx, r);
+    }
+    // w~_t' = alpha . w~ + y :  dot < (0.4528 t + 1) p, plus y < 1.886p
+    Fr neww;
+    {
+        uint32_t r[9], r8[8], lo[8], sum[9];
+        dot_mont<t>(
+            r, [&](int j, int k) { return T::tab(L::kAlpha + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+#pragma unroll
+        for (int k = 0; k < 8; k++) r8[k] = r[k];
+        uint32_t c = add8(lo, r8, y.l);
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum[k] = lo[k];
+        sum[8] = r[8] + c;
+        canon<canon_log2_for((t * 4528 + 28860 + 9999) / 10000)>(neww, sum);
+    }
+    // shift the words, the new one enters at the end
+#pragma unroll
+    for (int i = 0; i + 1 < t; i++) s[i] = s[i + 1];
+    s[t - 1] = neww;
+    s[t] = newx;
+}
+
+template <int W, class T, class Sync = NoSync>
+HADES_DEV void hades_perm_ccf(Fr (&s)[W]) {
+    typedef CcfLayout<W> L;
+    constexpr int kHalf = kFullRounds / 2;
+    constexpr int t = W - 1;
+#if !HADES_EMUL
+#pragma unroll 1
+#endif
+    for (int f = 0; f < kFullRounds; f++) {
+        full_round_opt<W, T>(s, L::kArk + f * W, (f == kHalf - 1) ? L::kPre : L::kMds);
+        Sync::sync();
+        if (f == kHalf - 1) {
+            add_table_vector<W, T>(s, L::kC4);
+#if !HADES_EMUL
+#pragma unroll 1
+#endif
+            for (int q = 0; q < kPartialRounds; q++) {
+                partial_round_ccf<W, T>(s, q);
+                Sync::sync();
+            }
+            // back to the original basis: w = P^-1 w~  (t rows of t-term dots, rotating output file)
+            Fr w[t];
+#pragma unroll
+            for (int i = 0; i < t; i++) w[i] = s[i];
+            HADES_NO_UNROLL
+            for (int row = 0; row < t; row++) {
+                uint32_t r[9];
+                const int base = L::kPinv + row * t;
+                dot_mont<t>(
+                    r, [&](int j, int k) { return T::tab(base + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+                Fr res;
+                canon<(t <= 6) ? 1 : 2>(res, r);
+                rotate_in<t>(w, res);
+            }
+#pragma unroll
+            for (int i = 0; i < t; i++) s[i] = w[i];
+        }
+    }
+}
+
 }  // namespace hades

@@ -43,7 +43,7 @@ thread_local std::string g_init_error;
 
 struct hades_ctx {
     uint32_t width = 0;
-    const WidthOps* ops2[2] = {nullptr, nullptr};  // [algo]
+    const WidthOps* ops2[3] = {nullptr, nullptr, nullptr};  // [algo]
     const WidthOps* ops() const { return ops2[variant.algo]; }
     bool generic() const { return ops2[0] == nullptr; }  // no tuned kernel for this width
     Variant variant = {1, 0};  // optimised schedule, <=128 registers
@@ -81,7 +81,8 @@ bool valid_dev(const hades_ctx* ctx, int dev_index) { return ctx && dev_index >=
 
 // Tables resident in __constant__ memory per (device ordinal, width): the reference's tables are
 // compile-time constants of the crate, so they are process-wide here as well.
-int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dense, const std::vector<uint64_t>& opt) {
+int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dense, const std::vector<uint64_t>& opt,
+                  const std::vector<uint64_t>& ccf) {
     std::lock_guard<std::mutex> lock(g_tables_mutex);
     auto it = g_tables.find({ordinal, (int)ctx->width});
     if (it != g_tables.end()) {
@@ -92,6 +93,7 @@ int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dens
     }
     CUDA_TRY(ctx, ctx->ops2[0]->upload(dense.data()));
     CUDA_TRY(ctx, ctx->ops2[1]->upload(opt.data()));
+    CUDA_TRY(ctx, ctx->ops2[2]->upload(ccf.data()));
     g_tables[{ordinal, (int)ctx->width}] = dense;
     return HADES_OK;
 }
@@ -167,16 +169,18 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
     if (tuned)
-        for (int a = 0; a < 2; a++) ctx->ops2[a] = width == 3 ? width_ops_3(a) : width == 5 ? width_ops_5(a) : width_ops_9(a);
+        for (int a = 0; a < 3; a++) ctx->ops2[a] = width == 3 ? width_ops_3(a) : width == 5 ? width_ops_5(a) : width_ops_9(a);
     ctx->variant = Variant{1, width == 9 ? 7 : 6};  // lockstep 128-thread blocks: x7 (W=3), x5 (W=5), x3 (W=9) per SM
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
-    std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt;
+    std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt, ccf;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
     int rc = HADES_OK;
     if (tuned) {
         if (dense.size() != ctx->ops2[0]->table_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
         if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops2[1]->table_u64))
             rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the sparse partial-round tables (singular MDS sub-matrix)");
+        if (rc == HADES_OK && (!hades_host::derive_tables_ccf((int)width, ark_limbs, mds_limbs, ccf) || ccf.size() != ctx->ops2[2]->table_u64))
+            rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the canonical-form tables (MDS block not controllable)");
     }
     for (int g = 0; g < n_dev && rc == HADES_OK; g++) {
         DeviceState d;
@@ -198,7 +202,7 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
                 CUDA_TRY(ctx, cudaMemcpy(d.generic_tables, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice));
                 return HADES_OK;
             }
-            return upload_tables(ctx, d.ordinal, dense, opt);
+            return upload_tables(ctx, d.ordinal, dense, opt, ccf);
         };
         rc = step();
     }
@@ -577,7 +581,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
 }
 
 int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
-    if (!ctx || algo < 0 || algo > 1 || regs < 0 || regs > 10) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
+    if (!ctx || algo < 0 || algo > 2 || regs < 0 || regs > 10) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     if (ctx->generic()) return fail(ctx, HADES_ERR_INVALID_ARG, "width %u runs the generic kernel, which has no variants", ctx->width);
     ctx->variant = Variant{algo, regs};
     return HADES_OK;

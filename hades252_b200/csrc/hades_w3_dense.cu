@@ -5,5 +5,8 @@
 namespace hades {
 const WidthOps* width_ops_3_dense() { return &kOps; }
 const WidthOps* width_ops_3_opt();
-const WidthOps* width_ops_3(int algo) { return algo == 0 ? width_ops_3_dense() : width_ops_3_opt(); }
+const WidthOps* width_ops_3_ccf();
+const WidthOps* width_ops_3(int algo) {
+    return algo == 0 ? width_ops_3_dense() : algo == 1 ? width_ops_3_opt() : width_ops_3_ccf();
+}
 }  // namespace hades

@@ -1,0 +1,7 @@
+// Width-5 kernels, canonical-form schedule (own translation unit = own 64 KB __constant__ bank).
+#define HADES_W 5
+#define HADES_ALGO 2
+#include "width_impl.cuh"
+namespace hades {
+const WidthOps* width_ops_5_ccf() { return &kOps; }
+}  // namespace hades

@@ -5,5 +5,8 @@
 namespace hades {
 const WidthOps* width_ops_5_dense() { return &kOps; }
 const WidthOps* width_ops_5_opt();
-const WidthOps* width_ops_5(int algo) { return algo == 0 ? width_ops_5_dense() : width_ops_5_opt(); }
+const WidthOps* width_ops_5_ccf();
+const WidthOps* width_ops_5(int algo) {
+    return algo == 0 ? width_ops_5_dense() : algo == 1 ? width_ops_5_opt() : width_ops_5_ccf();
+}
 }  // namespace hades

@@ -5,5 +5,8 @@
 namespace hades {
 const WidthOps* width_ops_9_dense() { return &kOps; }
 const WidthOps* width_ops_9_opt();
-const WidthOps* width_ops_9(int algo) { return algo == 0 ? width_ops_9_dense() : width_ops_9_opt(); }
+const WidthOps* width_ops_9_ccf();
+const WidthOps* width_ops_9(int algo) {
+    return algo == 0 ? width_ops_9_dense() : algo == 1 ? width_ops_9_opt() : width_ops_9_ccf();
+}
 }  // namespace hades

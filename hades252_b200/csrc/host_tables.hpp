@@ -29,6 +29,7 @@
 //                              to fit the 64 KB constant bank (short_b / short_row / short_dot below).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include <vector>
 
@@ -252,6 +253,105 @@ inline bool derive_tables(int W, const uint64_t* ark, const uint64_t* mds, std::
         for (int i = 0; i < t; i++) put_versions(sp[q].b[i], short_b(W));
     }
     return out.size() == table_entries(W) * 4;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Canonical-form schedule ("ccf", algo 2).  After the constant pushing above, the partial rounds are a
+// TIME-INVARIANT linear system driven by the S-box output s:   w' = A w + b s ,  x' = c^T w + d s
+// (A, b, c, d = blocks of the MDS matrix).  In the basis w~ = P w that puts (A, b) in controller canonical
+// form, A~ = P A P^-1 is a pure shift except for its last row alpha, and b~ = e_t.  A partial round is then
+//      w~_i <- w~_{i+1} (i < t: register renaming) ,  w~_t <- alpha . w~ + s ,  x <- c~ . w~ + d s
+// i.e. the same 2W-1 multiplications, but TWO reductions instead of W, no per-word update loop, and only
+// 2W-1 constants for all 59 rounds.  P is folded into the full round before (PRE = T M, T = diag(P, 1)); after
+// the last partial round the words are mapped back with one dense (W-1)x(W-1) multiply by P^-1.
+//
+// Table layout (entries of 4 u64): ARK_FULL (8W) | MDS (W*W) | PRE (W*W) | C4' (W) | e_q (59) | alpha (W-1) |
+// c~ (W-1) | d (1) | P^-1 ((W-1)^2, row-major).
+inline size_t ccf_table_entries(int W) {
+    return (size_t)kFull * W + 2 * (size_t)W * W + W + kPartial + 2 * (size_t)(W - 1) + 1 + (size_t)(W - 1) * (W - 1);
+}
+
+inline bool derive_tables_ccf(int W, const uint64_t* ark, const uint64_t* mds, std::vector<uint64_t>& out) {
+    const int t = W - 1;
+    auto getF = [](const uint64_t* p) { F f; for (int i = 0; i < 4; i++) f.l[i] = p[i]; return f; };
+    Mat M(W, Vec(W));
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < W; j++) M[i][j] = getF(mds + (size_t)(i * W + j) * 4);
+    std::vector<Vec> c(kFull + kPartial, Vec(W));
+    for (int r = 0; r < kFull + kPartial; r++)
+        for (int j = 0; j < W; j++) c[r][j] = getF(ark + (size_t)(r * W + j) * 4);
+    Mat A(t, Vec(t));
+    Vec b(t);
+    for (int i = 0; i < t; i++) {
+        for (int j = 0; j < t; j++) A[i][j] = M[i][j];
+        b[i] = M[i][t];
+    }
+    // Krylov vectors b, Ab, ..., A^t b;  A^t b = sum_j coef_j A^j b  (Cayley-Hamilton)
+    std::vector<Vec> kry(1, b);
+    for (int i = 0; i < t; i++) kry.push_back(matvec(A, kry.back()));
+    Mat K(t, Vec(t)), Kinv;
+    for (int i = 0; i < t; i++)
+        for (int j = 0; j < t; j++) K[i][j] = kry[j][i];
+    if (!invert(K, Kinv)) return false;  // (A, b) not controllable
+    Vec alpha = matvec(Kinv, kry[t]);
+    // columns v_1..v_t of P^-1:  v_t = b,  v_{j-1} = A v_j - alpha_j v_t
+    std::vector<Vec> v(t + 1);
+    v[t] = b;
+    for (int j = t; j > 1; j--) {
+        Vec Av = matvec(A, v[j]);
+        v[j - 1].resize(t);
+        for (int i = 0; i < t; i++) v[j - 1][i] = sub(Av[i], mul(alpha[j - 1], v[t][i]));
+    }
+    Mat Pinv(t, Vec(t)), Pm;
+    for (int i = 0; i < t; i++)
+        for (int j = 0; j < t; j++) Pinv[i][j] = v[j + 1][i];
+    if (!invert(Pinv, Pm)) return false;
+    Mat T(W, Vec(W, kZero)), Tinv(W, Vec(W, kZero));
+    for (int i = 0; i < t; i++)
+        for (int j = 0; j < t; j++) { T[i][j] = Pm[i][j]; Tinv[i][j] = Pinv[i][j]; }
+    T[t][t] = kOne;
+    Tinv[t][t] = kOne;
+    Mat Mt = matmul(matmul(T, M), Tinv);
+    // structure check: shift rows, unit input column
+    for (int i = 0; i + 1 < t; i++)
+        for (int j = 0; j < W; j++) {
+            const F& want = (j == i + 1) ? kOne : kZero;
+            if (memcmp(Mt[i][j].l, want.l, 32) != 0) return false;
+        }
+    if (memcmp(Mt[t - 1][t].l, kOne.l, 32) != 0) return false;
+    // constant pushing in the transformed coordinates
+    std::vector<Vec> ct(c.size());
+    for (size_t r = 0; r < c.size(); r++) ct[r] = matvec(T, c[r]);
+    Vec d(W, kZero), e(kPartial, kZero);
+    for (int q = 0; q + 1 < kPartial; q++) {
+        Vec u = matvec(Mt, d);
+        for (int j = 0; j < W; j++) u[j] = add(u[j], ct[kHalf + q + 1][j]);
+        e[q + 1] = u[t];
+        d = u;
+        d[t] = kZero;
+    }
+    Vec tail = matvec(Tinv, matvec(Mt, d));
+    Mat pre = matmul(T, M);
+    out.clear();
+    auto put = [&](const F& f) { for (int i = 0; i < 4; i++) out.push_back(f.l[i]); };
+    for (int r = 0; r < kHalf; r++)
+        for (int j = 0; j < W; j++) put(c[r][j]);
+    for (int j = 0; j < W; j++) put(add(c[kHalf + kPartial][j], tail[j]));
+    for (int r = kHalf + kPartial + 1; r < kFull + kPartial; r++)
+        for (int j = 0; j < W; j++) put(c[r][j]);
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < W; j++) put(M[i][j]);
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < W; j++) put(pre[i][j]);
+    for (int j = 0; j < W; j++) put(ct[kHalf][j]);
+    for (int q = 0; q < kPartial; q++) put(e[q]);
+    for (int j = 0; j < t; j++) put(Mt[t - 1][j]);  // alpha row
+    for (int j = 0; j < t; j++) put(Mt[t][j]);      // c~ row
+    put(Mt[t][t]);                                  // d
+    for (int i = 0; i < t; i++)
+        for (int j = 0; j < t; j++) put(Pinv[i][j]);
+    return out.size() == ccf_table_entries(W) * 4;
 }
 
 }  // namespace hades_host

@@ -4,7 +4,7 @@
 // multiplies, so these kernels are bound by the integer-multiply pipe, not by HBM.
 #pragma once
 #if !defined(HADES_W) || !defined(HADES_ALGO)
-#error "define HADES_W (3|5|9) and HADES_ALGO (0 dense | 1 optimised) before including width_impl.cuh"
+#error "define HADES_W (3|5|9) and HADES_ALGO (0 dense | 1 sparse | 2 canonical form) before including width_impl.cuh"
 #endif
 #include <string.h>
 
@@ -24,7 +24,7 @@ constexpr int kDenseEntries = kRounds * W + W * W;
 // One table per translation unit: the dense and the optimised kernels of a width live in separate TUs
 // (HADES_ALGO) because together their tables exceed the 64 KB constant bank.
 constexpr int kAlgo = HADES_ALGO;
-constexpr int kTableEntries = kAlgo == 0 ? kDenseEntries : Layout::kEntries;
+constexpr int kTableEntries = kAlgo == 0 ? kDenseEntries : kAlgo == 1 ? Layout::kEntries : CcfLayout<W>::kEntries;
 __constant__ uint32_t c_table[kTableEntries * 8];
 static_assert(sizeof(uint32_t) * kTableEntries * 8 + 32 <= 65536, "constant bank overflow");
 
@@ -37,11 +37,18 @@ struct OptTab {
     static __device__ __forceinline__ const uint32_t* ptr(int entry) { return c_table + entry * 8; }
 };
 
+// the fast schedules (1: sparse partial rounds, 2: canonical form), with or without the per-round barrier
+template <class Sync>
+__device__ __forceinline__ void permute_fast(Fr (&s)[W]) {
+    if constexpr (kAlgo == 2) hades_perm_ccf<W, OptTab, Sync>(s);
+    else hades_perm_opt<W, OptTab, Sync>(s);
+}
+
 template <int ALGO>
 __device__ __forceinline__ void permute(Fr (&s)[W]) {
     static_assert(ALGO == kAlgo, "this translation unit holds one algorithm");
     if constexpr (ALGO == 0) hades_perm<W, DenseConsts>(s);
-    else hades_perm_opt<W, OptTab>(s);
+    else permute_fast<NoSync>(s);
 }
 
 // 32-byte element <-> registers through two 128-bit accesses (pointers are 16-byte aligned).
@@ -69,7 +76,7 @@ __global__ void __launch_bounds__(kPermThreads, MINB) perm_batch_kernel(uint4* _
     for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
 }
 
-#if HADES_ALGO == 1
+#if HADES_ALGO >= 1
 // Lockstep variant: BLOCK threads per block, one barrier per round; out-of-range threads compute on the
 // last state and skip the store so that every thread reaches every barrier.
 struct BlockSync {
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) perm_batch_lockstep_kernel(uint4*
             }
         }
         __syncwarp();
-        hades_perm_opt<W, OptTab, BlockSync>(s);
+        permute_fast<BlockSync>(s);
         if (live) {
 #pragma unroll
             for (int j = 0; j < W; j++) fr_store(tile + lane * kStagePitch + 2 * j, s[j]);
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) perm_batch_lockstep_kernel(uint4*
         uint4* p = states + (i < n ? i : n - 1) * kChunksPerState;
 #pragma unroll
         for (int j = 0; j < W; j++) fr_load(s[j], p + 2 * j);
-        hades_perm_opt<W, OptTab, BlockSync>(s);
+        permute_fast<BlockSync>(s);
         if (i < n) {
 #pragma unroll
             for (int j = 0; j < W; j++) fr_store(p + 2 * j, s[j]);
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) perm_batch_lockstep_kernel(uint4*
     }
 }
 
-#endif  // HADES_ALGO == 1
+#endif  // HADES_ALGO >= 1
 
 #if HADES_W == 5
 // Montgomery forms of the two small constants the compositions need (checked in tests).
@@ -172,7 +179,7 @@ merkle_level_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_
     fr_store(out + i * 2, s[1]);
 }
 
-#if HADES_ALGO == 1
+#if HADES_ALGO >= 1
 // Lockstep Merkle level: same launch shape as the perm kernel (one barrier per round, no early exit); a
 // warp's 32 x 128 B of children are moved with coalesced 128-bit loads through padded shared memory.
 template <int BLOCK, int MINB>
@@ -200,10 +207,10 @@ merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ o
         if (n_in_warp > 0) fr_load(s[1 + j], mine + 2 * j);
         else fr_set_zero(s[1 + j]);
     }
-    hades_perm_opt<5, OptTab, BlockSync>(s);
+    permute_fast<BlockSync>(s);
     if (live) fr_store(out + (warp_first + lane) * 2, s[1]);
 }
-#endif  // HADES_ALGO == 1
+#endif  // HADES_ALGO >= 1
 
 // ---- sponge: rate 4 / capacity 1, one message per thread (CSR offsets) ------------------------------
 // `order` (optional) maps thread -> message so that a warp works on messages of equal block count.
@@ -240,7 +247,7 @@ sponge_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offs
     }
     fr_store(out + m * 2, s[1]);
 }
-#if HADES_ALGO == 1
+#if HADES_ALGO >= 1
 // Lockstep sponge: messages arrive sorted by permutation count (`order`), so the 128 messages of a block
 // almost always need the same number of perms.  Every thread runs the block's MAXIMUM count (one barrier per
 // round keeps the block on the same instruction-cache lines); a thread whose message ended earlier keeps
@@ -281,12 +288,12 @@ sponge_lockstep_kernel(const uint4* __restrict__ elems, const uint64_t* __restri
             }
             if (add) fr_add(s[1 + k], s[1 + k], x);
         }
-        hades_perm_opt<5, OptTab, BlockSync>(s);
+        permute_fast<BlockSync>(s);
         if (trip + 1 == my_blocks) digest = s[1];
     }
     if (live) fr_store(out + m * 2, digest);
 }
-#endif  // HADES_ALGO == 1
+#endif  // HADES_ALGO >= 1
 #endif  // HADES_W == 5
 
 // ---- host-side launchers ---------------------------------------------------------------------------
@@ -309,7 +316,7 @@ cudaError_t upload(const uint64_t* table) {
 
 cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-#if HADES_ALGO == 1
+#if HADES_ALGO >= 1
     if (v.regs >= 4) {  // lockstep launches: regs 4 -> 256 threads per block, 5 -> 512, 6.. experimental
         uint4* p = reinterpret_cast<uint4*>(d_states);
         switch (v.regs) {
@@ -345,7 +352,7 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
 #if HADES_W == 5
 cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s) {
     if (n_out == 0) return cudaSuccess;
-#if HADES_ALGO == 1
+#if HADES_ALGO >= 1
     if (v.regs >= 4) {  // lockstep launch shapes share one Merkle build
         merkle_level_lockstep_kernel<128, 5><<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(
             reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out);
@@ -364,14 +371,14 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
     if (n_threads == 0) return cudaSuccess;
     // lockstep shapes do not apply (messages differ in length); the optimised kernel fits 96 registers, so
     // use 5 blocks/SM (measured: 225 ms vs 249 ms at 4 blocks/SM for the 2^22-message config)
-#if HADES_ALGO == 1
+#if HADES_ALGO >= 1
     if (v.regs >= 4 && d_order != nullptr) {  // lockstep launch shapes: sorted messages, block-uniform trip counts
         sponge_lockstep_kernel<<<(unsigned)((n_threads + kPermThreads - 1) / kPermThreads), kPermThreads, 0, s>>>(
             reinterpret_cast<const uint4*>(d_elems), d_offsets, d_order, reinterpret_cast<uint4*>(d_out), n_threads);
         return cudaGetLastError();
     }
 #endif
-    if (v.regs >= 4) v.regs = (kAlgo == 1) ? 3 : 0;
+    if (v.regs >= 4) v.regs = (kAlgo >= 1) ? 3 : 0;
     size_t blocks = (n_threads + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     HADES_DISPATCH(sponge_kernel, v,
@@ -388,7 +395,7 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
                      : cudaFuncGetAttributes(out, KERNEL<kAlgo, 5>))
 
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
-#if HADES_ALGO == 1
+#if HADES_ALGO >= 1
     if (!strcmp(kernel, "perm") && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);
     if (!strcmp(kernel, "perm") && v.regs == 5) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<512, 1>);
 #if HADES_W == 9
@@ -408,7 +415,7 @@ cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* o
 #if HADES_W == 5
     if (!strcmp(kernel, "merkle") && v.regs >= 4) return cudaFuncGetAttributes(out, merkle_level_lockstep_kernel<128, 5>);
 #endif
-#endif  // HADES_ALGO == 1
+#endif  // HADES_ALGO >= 1
     if (v.regs >= 4) v.regs = 0;  // sponge / dense: plain 128-thread launches
     if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);
 #if HADES_W == 5

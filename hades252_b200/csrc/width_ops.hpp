@@ -11,6 +11,7 @@ namespace hades {
 // Kernel variants (runtime-selectable so that bench/tests can A/B them; all bit-identical):
 //   algo 0 = dense schedule (reference round structure, one lazily reduced dot product per MDS row)
 //   algo 1 = optimised schedule (sparse partial rounds, host_tables.hpp)
+//   algo 2 = canonical-form schedule (time-invariant partial rounds in controller form, host_tables.hpp)
 //   regs 0 = __launch_bounds__(128, 4) (<=128 registers), 1 = (128, 3) (<=168), 2 = (128, 2) (<=255),
 //   3 = (128, 5) (<=96); 4 / 5 = lockstep blocks of 256 / 512 threads with one barrier per round;
 //   6.. = lockstep 128-thread blocks (W=5: 6 -> 5 blocks/SM [default], 9 -> 4; W=3: 6 -> 7 [default], 7 -> 5;
@@ -24,7 +25,7 @@ constexpr int kPermThreads = 128;
 
 struct WidthOps {
     int width;
-    int algo;          // 0: dense table (67*W + W*W entries); 1: optimised table (OptLayout<W>::kEntries)
+    int algo;          // 0: dense table (67*W + W*W entries); 1: OptLayout<W>::kEntries; 2: CcfLayout<W>::kEntries
     size_t table_u64;  // entries * 4
     cudaError_t (*upload)(const uint64_t* table);  // to the CURRENT device
     cudaError_t (*launch_perm)(Variant v, uint64_t* d_states, size_t n, cudaStream_t s);
@@ -35,7 +36,7 @@ struct WidthOps {
     cudaError_t (*func_attributes)(const char* kernel, Variant v, cudaFuncAttributes* out);
 };
 
-// one translation unit per (width, algo): hades_w{3,5,9}.cu (optimised) and hades_w{3,5,9}_dense.cu
+// one translation unit per (width, algo): hades_w{3,5,9}.cu (sparse), _dense.cu, _ccf.cu
 const WidthOps* width_ops_3(int algo);
 const WidthOps* width_ops_5(int algo);
 const WidthOps* width_ops_9(int algo);

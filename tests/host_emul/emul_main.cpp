@@ -29,6 +29,13 @@ struct HostTab {
     static const uint32_t* ptr(int entry) { return reinterpret_cast<const uint32_t*>(g_opt[W].data()) + (size_t)entry * 8; }
 };
 
+static std::vector<uint64_t> g_ccf[10];
+template <int W>
+struct HostTabCcf {
+    static uint32_t tab(int entry, int k) { return (uint32_t)(g_ccf[W][(size_t)entry * 4 + k / 2] >> (32 * (k & 1))); }
+    static const uint32_t* ptr(int entry) { return reinterpret_cast<const uint32_t*>(g_ccf[W].data()) + (size_t)entry * 8; }
+};
+
 static uint64_t rng_state = 0x1234567;
 static uint64_t rnd() {
     uint64_t z = (rng_state += 0x9e3779b97f4a7c15ULL);
@@ -55,8 +62,9 @@ static int check_perm(int iters) {
         for (int j = 0; j < W; j++) rand_fr(st + 4 * j, it < 40 ? (it + j) % 5 : 0);
         hades::Fr s[W];
         for (int j = 0; j < W; j++) to32(s[j], st + 4 * j);
-        hades::Fr s2[W];
-        for (int j = 0; j < W; j++) s2[j] = s[j];
+        hades::Fr s2[W], s3[W];
+        for (int j = 0; j < W; j++) s3[j] = s2[j] = s[j];
+        hades::hades_perm_ccf<W, HostTabCcf<W>>(s3);
         hades::hades_perm<W, HostConsts<W>>(s);
         hades::hades_perm_opt<W, HostTab<W>>(s2);
         oracle_perm(st, W, g_ark.data(), g_mds[W].data());
@@ -65,6 +73,8 @@ static int check_perm(int iters) {
             if (memcmp(got, st + 4 * j, 32)) { printf("perm W=%d mismatch iter %d word %d\n", W, it, j); return 1; }
             to64(got, s2[j]);
             if (memcmp(got, st + 4 * j, 32)) { printf("perm_opt W=%d mismatch iter %d word %d\n", W, it, j); return 1; }
+            to64(got, s3[j]);
+            if (memcmp(got, st + 4 * j, 32)) { printf("perm_ccf W=%d mismatch iter %d word %d\n", W, it, j); return 1; }
         }
     }
     return 0;
@@ -82,6 +92,10 @@ int main(int argc, char** argv) {
         if (!hades_host::derive_tables(w, g_ark.data(), g_mds[w].data(), g_opt[w])) { printf("derive_tables(%d) failed\n", w); return 1; }
         if (g_opt[w].size() != (size_t)hades::OptLayout<3>::kEntries * 0 + hades_host::table_entries(w) * 4) return 1;
     }
+    for (int w : {3, 5, 9})
+        if (!hades_host::derive_tables_ccf(w, g_ark.data(), g_mds[w].data(), g_ccf[w])) { printf("derive_tables_ccf(%d) failed\n", w); return 1; }
+    if (hades_host::ccf_table_entries(5) != (size_t)hades::CcfLayout<5>::kEntries || hades_host::ccf_table_entries(9) != (size_t)hades::CcfLayout<9>::kEntries ||
+        hades_host::ccf_table_entries(3) != (size_t)hades::CcfLayout<3>::kEntries) { printf("ccf layout mismatch\n"); return 1; }
     if (hades_host::table_entries(5) != (size_t)hades::OptLayout<5>::kEntries || hades_host::table_entries(9) != (size_t)hades::OptLayout<9>::kEntries ||
         hades_host::table_entries(3) != (size_t)hades::OptLayout<3>::kEntries) { printf("layout mismatch\n"); return 1; }
     if (argc > 2) {  // dump the derived tables for the Python cross-check

@@ -26,7 +26,7 @@ def test_extension_loaded_and_kernels_spill_free(cuda_strategy):
     print("perm5", info, "merkle", cuda_strategy.kernel_info("merkle"), "sponge", cuda_strategy.kernel_info("sponge"))
 
 
-@pytest.mark.parametrize("algo,regs", [(0, 0), (0, 1), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (1, 5)])
+@pytest.mark.parametrize("algo,regs", [(0, 0), (0, 1), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (2, 0), (2, 3), (2, 6), (2, 9)])
 def test_all_kernel_variants_bit_identical(oracle, algo, regs):
     """dense schedule (reference round structure) vs sparse-partial-round schedule, all register
     budgets: same bits as the oracle, for perm, merkle and sponge."""
@@ -49,7 +49,7 @@ def test_all_kernel_variants_bit_identical(oracle, algo, regs):
 
 
 @pytest.mark.parametrize("w", [3, 9])
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_other_widths_both_schedules(oracle, w, algo):
     from hades252_b200 import CudaStrategy
     n = 2000

@@ -4,7 +4,7 @@ python - <<'PY'
 import torch, time
 from hades252_b200 import CudaStrategy
 stream = torch.cuda.current_stream(); sp = stream.cuda_stream
-for w, variants in ((3, [(1,4),(1,6),(1,7),(1,0),(1,3)]), (9, [(1,2),(1,6),(1,7),(1,1)])):
+for w, variants in ((3, [(1,6),(2,6),(2,7)]), (9, [(1,7),(2,7),(2,6),(2,2)])):
     s = CudaStrategy([0], width=w)
     n = 1 << 22
     buf = torch.empty(n * w * 4, dtype=torch.int64, device="cuda")
