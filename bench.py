@@ -36,10 +36,13 @@ sys.path.insert(0, ROOT)
 
 WIDTH = 5
 LIMB_PRODUCTS_PER_PERM = 268192   # 1972 Fr mul x 136 (8-limb CIOS), SURVEY.md 8(d)
-# IMAD.WIDE products the default kernel actually executes per perm:
-#   partial round: x^5 2*(36+48) + (64+48) = 280; 5-term dot 5*64+48 = 368; 4 short-reduced b products 4*(64+12) = 304
-#   -> 952, x59; full round 5*280 + 5*368 = 3240, x8
-EXECUTED_PRODUCTS_PER_PERM = 59 * 952 + 8 * 3240
+# IMAD.WIDE products the kernels actually execute per perm; x^5 = 2*(36+48) + (64+48) = 280,
+# an N-term lazily reduced dot product = 64 N + 48.
+#   default (algo 2, gauged canonical form): partial round 280 + 2 x 4-term dot (304) = 888, x59;
+#     full rounds 0..6: 5*280 + 5*304 = 2920; full round 7 (dense): 5*280 + 5*368 = 3240; P^-1 stage 4 x 3-term dot = 960
+#   algo 1 (sparse partial rounds): partial 280 + 368 + 4 short-reduced b products 4*(64+12) = 952, x59; full 3240, x8
+EXECUTED_PRODUCTS = {2: 59 * 888 + 7 * 2920 + 3240 + 960, 1: 59 * 952 + 8 * 3240}
+EXECUTED_PRODUCTS_PER_PERM = EXECUTED_PRODUCTS[2]
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE default-kernel launch over 2^26 states, from the
 # `ncu --set full` capture summarised in profiles/r01_ncu_perm5_2p26_final.txt (10.847 + 10.706 GB)
 NCU_TRAFFIC_BYTES_2P26 = 21_552_996_000
@@ -336,6 +339,7 @@ def run_ours(args):
         pk, pk_src = measured_peaks()
         per_gpu = value / world
         achieved = per_gpu * LIMB_PRODUCTS_PER_PERM / 1e12
+        executed_products = EXECUTED_PRODUCTS.get(int(args.variant.split(",")[0])) if args.variant else EXECUTED_PRODUCTS_PER_PERM
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -351,11 +355,11 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": n * HBM_BYTES_PER_PERM,
                          "kernel": "perm_batch_kernel (width 5)", "variant": args.variant or "default", "kernel_ms": kernel_ms,
                          "algorithmic_products_per_perm": LIMB_PRODUCTS_PER_PERM,
-                         "executed_products_per_perm": EXECUTED_PRODUCTS_PER_PERM if not args.variant else None,
-                         "executed_frac": (per_gpu * EXECUTED_PRODUCTS_PER_PERM / p_mul32) if not args.variant else None,
+                         "executed_products_per_perm": executed_products,
+                         "executed_frac": (per_gpu * executed_products / p_mul32) if executed_products else None,
                          "note": "frac uses the ALGORITHMIC count (dense reference algorithm, SURVEY 8(d)) and exceeds 1 "
-                                 "because the kernel executes ~3x fewer products (sparse partial rounds, lazy reduction, "
-                                 "squaring); executed_frac is the pipe-level utilisation and agrees with ncu "
+                                 "because the kernel executes ~3.5x fewer products (canonical-form partial rounds, diagonal "
+                                 "gauge, lazy reduction, squaring); executed_frac is the pipe-level utilisation and agrees with ncu "
                                  "sm__pipe_fmaheavy_cycles_active",
                          "peak_source": "hades_imad_peak live on this device",
                          "peak_variants_Tprod_s": {names[v]: peaks[v] / 1e12 for v in peaks}},

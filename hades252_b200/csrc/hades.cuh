@@ -277,61 +277,103 @@ HADES_DEV void hades_perm_opt(Fr (&s)[W]) {
 
 
 // ------------------------------------------------------------------------------------------------
-// Canonical-form schedule (algo 2; derivation in host_tables.hpp, derive_tables_ccf): per partial round
-//   x += e_q ; s = x^5 ; w~_t' = alpha . w~ + s ; x' = c~ . w~ + d s ; w~_i' = w~_{i+1}
-// Same multiplications as the sparse schedule, two reductions instead of W, no per-word loop.
+// Canonical-form schedule with a diagonal gauge (algo 2; derivation in host_tables.hpp, derive_tables_ccf).
+// Every word is kept multiplied by a host-chosen scalar so that one matrix entry per output row is 1:
+//   full rounds 0..6:   row_i = s_0 + sum_{j>=1} M^_f[i][j] s_j          (W-1 products per row)
+//   partial round q:    x += e_q ; y = x^5 ; w_t' = alpha_q . w + y ; x' = c_q . w + y ; w_i' = w_{i+1}
+//   P^-1 stage:         z_i = w_0 + sum_{j>=1} Q[i][j] w_j
+//   full round 7:       dense (removes the gauge)
 // ------------------------------------------------------------------------------------------------
 template <int W>
 struct CcfLayout {
     static constexpr int t = W - 1;
     static constexpr int kArk = 0;
-    static constexpr int kMds = kFullRounds * W;
-    static constexpr int kPre = kMds + W * W;
-    static constexpr int kC4 = kPre + W * W;
-    static constexpr int kE = kC4 + W;
-    static constexpr int kAlpha = kE + kPartialRounds;
-    static constexpr int kCrow = kAlpha + t;
-    static constexpr int kD = kCrow + t;
-    static constexpr int kPinv = kD + 1;
-    static constexpr int kEntries = kPinv + t * t;
-    // the full rounds reuse full_round_opt, which expects OptLayout's kShortRow == 1 layout of dense matrices
+    static constexpr int kMat = kFullRounds * W;                 // 7 matrices of W x (W-1)
+    static constexpr int kMatStride = W * t;
+    static constexpr int kLast = kMat + (kFullRounds - 1) * kMatStride;  // W x W
+    static constexpr int kC4 = kLast + W * W;
+    static constexpr int kPart = kC4 + W;                        // 59 x { e, alpha[t], c[t] }
+    static constexpr int kPartStride = 2 * t + 1;
+    static constexpr int kPinv = kPart + kPartialRounds * kPartStride;  // t x (t-1)
+    static constexpr int kEntries = kPinv + t * (t - 1);
 };
 
+// r (9 limbs) += v (8 limbs)
+HADES_DEV void add_into9(uint32_t (&r)[9], const Fr& v) {
+    uint32_t r8[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) r8[k] = r[k];
+    uint32_t c = add8(lo, r8, v.l);
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = lo[k];
+    r[8] += c;
+}
+
+// out_i = s_0 + sum_{j=1..N-1} tab[base + i*(N-1) + j-1] * s_j  for i < ROWS, written into the first ROWS
+// words of s (rotating output file; words ROWS..N-1 keep their values).  Inputs canonical.
+// Bound: 1 + (1 + 0.4528 (N-1)):  N <= 5 -> < 4p, N <= 13 -> < 8p.
+template <int N, int ROWS, class T>
+HADES_DEV void unit_column_rows(Fr (&s)[N], int base) {
+    static_assert(N >= 2 && N <= 13 && ROWS <= N, "bounds above");
+    Fr out[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; j++) out[j] = s[j];  // placeholders, all overwritten
+    HADES_NO_UNROLL
+    for (int row = 0; row < ROWS; row++) {
+        uint32_t r[9];
+        const int b = base + row * (N - 1);
+        dot_mont<N - 1>(
+            r, [&](int j, int k) { return T::tab(b + j, k); }, [&](int j, int i) { return s[j + 1].l[i]; });
+        add_into9(r, s[0]);
+        Fr res;
+        canon<(N <= 5) ? 1 : 2>(res, r);
+        rotate_in<ROWS>(out, res);
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; j++) s[j] = out[j];
+}
+
+// ARK + S-box on every word (W trips on word 0, rotating), constants at table entry `ark`
 template <int W, class T>
-HADES_DEV void partial_round_ccf(Fr (&s)[W], int q) {
-    typedef CcfLayout<W> L;
+HADES_DEV void ark_sbox_all(Fr (&s)[W], int ark) {
+    HADES_NO_UNROLL
+    for (int j = 0; j < W; j++) {
+        Fr c, x = s[0];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c.l[k] = T::tab(ark + j, k);
+        fr_add(x, x, c);
+        fr_sbox(x);
+        rotate_in<W>(s, x);
+    }
+}
+
+template <int W, class T>
+HADES_DEV void partial_round_ccf(Fr (&s)[W], int base) {
     constexpr int t = W - 1;
     {
         Fr e;
 #pragma unroll
-        for (int k = 0; k < 8; k++) e.l[k] = T::tab(L::kE + q, k);
+        for (int k = 0; k < 8; k++) e.l[k] = T::tab(base, k);
         fr_add(s[t], s[t], e);
     }
     Fr y, x4;
     fr_pow4_lazy(x4, s[t]);
-    fr_mul_lazy(y, x4, s[t]);  // < 1.886p
-    // x' = c~ . w~ + d y   (bounds as in the sparse schedule)
-    Fr newx;
+    fr_mul(y, x4, s[t]);  // canonical: it is added to both dot products below
+    // both new words: (t-term dot) + y  <  (1 + 0.4528 t) p + p
+    Fr newx, neww;
     {
         uint32_t r[9];
-        dot_mont<W>(
-            r, [&](int j, int k) { return j < t ? T::tab(L::kCrow + j, k) : T::tab(L::kD, k); },
-            [&](int j, int i) { return j < t ? s[j].l[i] : y.l[i]; });
+        dot_mont<t>(
+            r, [&](int j, int k) { return T::tab(base + 1 + t + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+        add_into9(r, y);
         canon<(W <= 5) ? 1 : 2>(newx, r);
     }
-    // w~_t' = alpha . w~ + y :  dot < (0.4528 t + 1) p, plus y < 1.886p
-    Fr neww;
     {
-        uint32_t r[9], r8[8], lo[8], sum[9];
+        uint32_t r[9];
         dot_mont<t>(
-            r, [&](int j, int k) { return T::tab(L::kAlpha + j, k); }, [&](int j, int i) { return s[j].l[i]; });
-#pragma unroll
-        for (int k = 0; k < 8; k++) r8[k] = r[k];
-        uint32_t c = add8(lo, r8, y.l);
-#pragma unroll
-        for (int k = 0; k < 8; k++) sum[k] = lo[k];
-        sum[8] = r[8] + c;
-        canon<canon_log2_for((t * 4528 + 28860 + 9999) / 10000)>(neww, sum);
+            r, [&](int j, int k) { return T::tab(base + 1 + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+        add_into9(r, y);
+        canon<(W <= 5) ? 1 : 2>(neww, r);
     }
     // shift the words, the new one enters at the end
 #pragma unroll
@@ -348,8 +390,9 @@ HADES_DEV void hades_perm_ccf(Fr (&s)[W]) {
 #if !HADES_EMUL
 #pragma unroll 1
 #endif
-    for (int f = 0; f < kFullRounds; f++) {
-        full_round_opt<W, T>(s, L::kArk + f * W, (f == kHalf - 1) ? L::kPre : L::kMds);
+    for (int f = 0; f + 1 < kFullRounds; f++) {
+        ark_sbox_all<W, T>(s, L::kArk + f * W);
+        unit_column_rows<W, W, T>(s, L::kMat + f * L::kMatStride);
         Sync::sync();
         if (f == kHalf - 1) {
             add_table_vector<W, T>(s, L::kC4);
@@ -357,27 +400,44 @@ HADES_DEV void hades_perm_ccf(Fr (&s)[W]) {
 #pragma unroll 1
 #endif
             for (int q = 0; q < kPartialRounds; q++) {
-                partial_round_ccf<W, T>(s, q);
+                partial_round_ccf<W, T>(s, L::kPart + q * L::kPartStride);
                 Sync::sync();
             }
-            // back to the original basis: w = P^-1 w~  (t rows of t-term dots, rotating output file)
+            // back to the original basis (gauged): z_i = w_0 + sum_{j>=1} Q[i][j] w_j ; the last word stays
             Fr w[t];
 #pragma unroll
             for (int i = 0; i < t; i++) w[i] = s[i];
-            HADES_NO_UNROLL
-            for (int row = 0; row < t; row++) {
-                uint32_t r[9];
-                const int base = L::kPinv + row * t;
-                dot_mont<t>(
-                    r, [&](int j, int k) { return T::tab(base + j, k); }, [&](int j, int i) { return s[j].l[i]; });
-                Fr res;
-                canon<(t <= 6) ? 1 : 2>(res, r);
-                rotate_in<t>(w, res);
-            }
+            unit_column_rows<t, t, T>(w, L::kPinv);
 #pragma unroll
             for (int i = 0; i < t; i++) s[i] = w[i];
         }
     }
+    // last full round: dense rows, lands on the true state.  Rows 0..W-2 go through a rotating file of
+    // W-1 words and the last row is peeled, so at most 2W-1 words are live (register budget: 96 at W = 5).
+    ark_sbox_all<W, T>(s, L::kArk + (kFullRounds - 1) * W);
+    {
+        auto dense_row = [&](Fr& res, int b) {
+            uint32_t r[9];
+            dot_mont<W>(
+                r, [&](int j, int k) { return T::tab(b + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+            canon<(W <= 6) ? 1 : 2>(res, r);
+        };
+        Fr out[t];
+#pragma unroll
+        for (int j = 0; j < t; j++) out[j] = s[j];
+        HADES_NO_UNROLL
+        for (int row = 0; row < t; row++) {
+            Fr res;
+            dense_row(res, L::kLast + row * W);
+            rotate_in<t>(out, res);
+        }
+        Fr last;
+        dense_row(last, L::kLast + t * W);
+#pragma unroll
+        for (int j = 0; j < t; j++) s[j] = out[j];
+        s[t] = last;
+    }
+    Sync::sync();
 }
 
 }  // namespace hades

@@ -47,6 +47,7 @@ struct hades_ctx {
     const WidthOps* ops() const { return ops2[variant.algo]; }
     bool generic() const { return ops2[0] == nullptr; }  // no tuned kernel for this width
     Variant variant = {1, 0};  // optimised schedule, <=128 registers
+    bool has_ccf = false;      // canonical-form tables derived (algo 2 available)
     std::vector<DeviceState> devs;
     mutable std::string err;
     uint64_t launches = 0;
@@ -93,7 +94,7 @@ int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dens
     }
     CUDA_TRY(ctx, ctx->ops2[0]->upload(dense.data()));
     CUDA_TRY(ctx, ctx->ops2[1]->upload(opt.data()));
-    CUDA_TRY(ctx, ctx->ops2[2]->upload(ccf.data()));
+    if (!ccf.empty()) CUDA_TRY(ctx, ctx->ops2[2]->upload(ccf.data()));
     g_tables[{ordinal, (int)ctx->width}] = dense;
     return HADES_OK;
 }
@@ -179,8 +180,13 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
         if (dense.size() != ctx->ops2[0]->table_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
         if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops2[1]->table_u64))
             rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the sparse partial-round tables (singular MDS sub-matrix)");
-        if (rc == HADES_OK && (!hades_host::derive_tables_ccf((int)width, ark_limbs, mds_limbs, ccf) || ccf.size() != ctx->ops2[2]->table_u64))
-            rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the canonical-form tables (MDS block not controllable)");
+        // The gauged canonical-form schedule (default) needs a controllable MDS block and non-zero pivots; with
+        // constants where that fails (never with the reference's assets) the sparse schedule stays the default.
+        if (rc == HADES_OK) {
+            ctx->has_ccf = hades_host::derive_tables_ccf((int)width, ark_limbs, mds_limbs, ccf) && ccf.size() == ctx->ops2[2]->table_u64;
+            if (!ctx->has_ccf) ccf.clear();
+            else ctx->variant.algo = 2;
+        }
     }
     for (int g = 0; g < n_dev && rc == HADES_OK; g++) {
         DeviceState d;
@@ -583,6 +589,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
 int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
     if (!ctx || algo < 0 || algo > 2 || regs < 0 || regs > 10) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     if (ctx->generic()) return fail(ctx, HADES_ERR_INVALID_ARG, "width %u runs the generic kernel, which has no variants", ctx->width);
+    if (algo == 2 && !ctx->has_ccf) return fail(ctx, HADES_ERR_CONSTANTS, "the canonical-form schedule could not be derived for these constants");
     ctx->variant = Variant{algo, regs};
     return HADES_OK;
 }

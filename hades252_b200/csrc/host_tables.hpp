@@ -262,14 +262,29 @@ inline bool derive_tables(int W, const uint64_t* ark, const uint64_t* mds, std::
 // (A, b, c, d = blocks of the MDS matrix).  In the basis w~ = P w that puts (A, b) in controller canonical
 // form, A~ = P A P^-1 is a pure shift except for its last row alpha, and b~ = e_t.  A partial round is then
 //      w~_i <- w~_{i+1} (i < t: register renaming) ,  w~_t <- alpha . w~ + s ,  x <- c~ . w~ + d s
-// i.e. the same 2W-1 multiplications, but TWO reductions instead of W, no per-word update loop, and only
-// 2W-1 constants for all 59 rounds.  P is folded into the full round before (PRE = T M, T = diag(P, 1)); after
-// the last partial round the words are mapped back with one dense (W-1)x(W-1) multiply by P^-1.
+// i.e. TWO dot products with two reductions instead of W, and no per-word update loop.  P is folded into the
+// full round before (PRE = T M, T = diag(P, 1)); after the last partial round the words are mapped back with
+// one dense (W-1)x(W-1) multiply by P^-1.
 //
-// Table layout (entries of 4 u64): ARK_FULL (8W) | MDS (W*W) | PRE (W*W) | C4' (W) | e_q (59) | alpha (W-1) |
-// c~ (W-1) | d (1) | P^-1 ((W-1)^2, row-major).
+// Diagonal gauge.  x -> x^5 commutes with scaling up to a constant: (lambda x)^5 = lambda^5 x^5.  The kernel
+// therefore keeps every word multiplied by a host-chosen non-zero scalar (the "gauge", different per word and
+// per round), and the scalars are chosen so that as many matrix entries as possible become exactly 1:
+//   * full rounds 0..6:  z^' = G' M G^-5 S(z^ + G c)  with G' chosen so that COLUMN 0 of G' M G^-5 is all
+//     ones: every output row is  s_0 + (W-1)-term dot  instead of a W-term dot (W products fewer per round);
+//     the last full round has to land on the true state (G' = I) and stays dense;
+//   * partial rounds:  x^_q = lambda_q x_q,  w^_{q,i} = nu_{q+i} w~_{q,i}  (a function of q+i, so the shift
+//     stays a pure renaming) with  nu_{q+1+t} = lambda_q^5  and  lambda_{q+1} = lambda_q^5 / d : the S-box
+//     output then enters BOTH new words with coefficient 1,
+//         w^_t' = alpha_q . w^ + s^ ,   x^' = c_q . w^ + s^        (2W-2 multiplications per partial round),
+//     at the price of per-round constants alpha_q, c_q (59 x (2W-1) entries with e_q);
+//   * the P^-1 stage is followed by a full round, so its rows are gauged too (column 0 all ones).
+// Every transformation is exact in F_p and the last round removes the gauge, so outputs are bit-identical.
+//
+// Table layout (entries of 4 u64): ARK (8W, gauged) | 7 matrices of W x (W-1) (rows without column 0) |
+// last matrix W x W | C4' (W) | 59 x { e_q, alpha_q[W-1], c_q[W-1] } | P^-1 gauged, (W-1) x (W-2).
 inline size_t ccf_table_entries(int W) {
-    return (size_t)kFull * W + 2 * (size_t)W * W + W + kPartial + 2 * (size_t)(W - 1) + 1 + (size_t)(W - 1) * (W - 1);
+    const size_t t = W - 1;
+    return (size_t)kFull * W + (size_t)(kFull - 1) * W * t + (size_t)W * W + W + (size_t)kPartial * (2 * t + 1) + t * (t - 1);
 }
 
 inline bool derive_tables_ccf(int W, const uint64_t* ark, const uint64_t* mds, std::vector<uint64_t>& out) {
@@ -333,24 +348,94 @@ inline bool derive_tables_ccf(int W, const uint64_t* ark, const uint64_t* mds, s
     }
     Vec tail = matvec(Tinv, matvec(Mt, d));
     Mat pre = matmul(T, M);
+    // ---- diagonal gauge -------------------------------------------------------------------------------
+    auto pow5 = [](const F& x) { F x2 = mul(x, x); return mul(mul(x2, x2), x); };
+    bool ok = true;
+    // B = base * diag(g)^-5, then rows scaled so that column 0 is 1 (unit == true); g <- the row scalings
+    auto gauge_matrix = [&](const Mat& base, Vec& g, bool unit) {
+        const size_t n = base.size(), m = base[0].size();
+        Mat B(n, Vec(m));
+        for (size_t j = 0; j < m; j++) {
+            F s = inv(pow5(g[j]));
+            for (size_t i = 0; i < n; i++) B[i][j] = mul(base[i][j], s);
+        }
+        Vec gn(n, kOne);
+        if (unit)
+            for (size_t i = 0; i < n; i++) {
+                if (is_zero(B[i][0])) { ok = false; return B; }
+                gn[i] = inv(B[i][0]);
+                for (size_t j = 0; j < m; j++) B[i][j] = mul(B[i][j], gn[i]);
+            }
+        g = gn;
+        return B;
+    };
+    std::vector<Vec> arkfull(kFull);
+    for (int r = 0; r < kHalf; r++) arkfull[r] = c[r];
+    arkfull[kHalf] = c[kHalf + kPartial];
+    for (int j = 0; j < W; j++) arkfull[kHalf][j] = add(arkfull[kHalf][j], tail[j]);
+    for (int r = kHalf + 1; r < kFull; r++) arkfull[r] = c[kPartial + r];
+    std::vector<Vec> ark_g(kFull, Vec(W));
+    std::vector<Mat> mat_g(kFull);
+    Vec g(W, kOne);
+    for (int f = 0; f < kHalf; f++) {
+        for (int j = 0; j < W; j++) ark_g[f][j] = mul(g[j], arkfull[f][j]);
+        mat_g[f] = gauge_matrix(f == kHalf - 1 ? pre : M, g, true);
+        if (!ok) return false;
+    }
+    // g = gauge of (w~_1..w~_t, x) entering the partial rounds
+    Vec c4(W);
+    for (int j = 0; j < W; j++) c4[j] = mul(g[j], ct[kHalf][j]);
+    std::vector<F> nu(kPartial + t + 1, kOne);  // nu[k], k = 1 .. 59 + t
+    for (int i = 1; i <= t; i++) nu[i] = g[i - 1];
+    F lam = g[t];
+    if (is_zero(Mt[t][t])) return false;
+    const F dinv = inv(Mt[t][t]);
+    std::vector<F> e_g(kPartial);
+    std::vector<Vec> alpha_g(kPartial, Vec(t)), crow_g(kPartial, Vec(t));
+    for (int q = 0; q < kPartial; q++) {
+        e_g[q] = mul(lam, e[q]);
+        const F l5 = pow5(lam);
+        nu[q + 1 + t] = l5;
+        const F lam_next = mul(l5, dinv);
+        for (int j = 1; j <= t; j++) {
+            const F ninv = inv(nu[q + j]);
+            alpha_g[q][j - 1] = mul(mul(l5, Mt[t - 1][j - 1]), ninv);
+            crow_g[q][j - 1] = mul(mul(lam_next, Mt[t][j - 1]), ninv);
+        }
+        lam = lam_next;
+    }
+    // P^-1 stage: z_i = sum_j Pinv[i][j] w~_j = sum_j (Pinv[i][j] / nu[59 + j + 1]) w^_j ; rows gauged to unit column 0
+    Mat pinv_g(t, Vec(t));
+    for (int j = 0; j < t; j++) {
+        const F ninv = inv(nu[kPartial + j + 1]);
+        for (int i = 0; i < t; i++) pinv_g[i][j] = mul(Pinv[i][j], ninv);
+    }
+    for (int i = 0; i < t; i++) {
+        if (is_zero(pinv_g[i][0])) return false;
+        g[i] = inv(pinv_g[i][0]);
+        for (int j = 0; j < t; j++) pinv_g[i][j] = mul(pinv_g[i][j], g[i]);
+    }
+    g[t] = lam;
+    for (int f = kHalf; f < kFull; f++) {
+        for (int j = 0; j < W; j++) ark_g[f][j] = mul(g[j], arkfull[f][j]);
+        mat_g[f] = gauge_matrix(M, g, f + 1 < kFull);
+        if (!ok) return false;
+    }
     out.clear();
     auto put = [&](const F& f) { for (int i = 0; i < 4; i++) out.push_back(f.l[i]); };
-    for (int r = 0; r < kHalf; r++)
-        for (int j = 0; j < W; j++) put(c[r][j]);
-    for (int j = 0; j < W; j++) put(add(c[kHalf + kPartial][j], tail[j]));
-    for (int r = kHalf + kPartial + 1; r < kFull + kPartial; r++)
-        for (int j = 0; j < W; j++) put(c[r][j]);
-    for (int i = 0; i < W; i++)
-        for (int j = 0; j < W; j++) put(M[i][j]);
-    for (int i = 0; i < W; i++)
-        for (int j = 0; j < W; j++) put(pre[i][j]);
-    for (int j = 0; j < W; j++) put(ct[kHalf][j]);
-    for (int q = 0; q < kPartial; q++) put(e[q]);
-    for (int j = 0; j < t; j++) put(Mt[t - 1][j]);  // alpha row
-    for (int j = 0; j < t; j++) put(Mt[t][j]);      // c~ row
-    put(Mt[t][t]);                                  // d
+    for (int f = 0; f < kFull; f++)
+        for (int j = 0; j < W; j++) put(ark_g[f][j]);
+    for (int f = 0; f < kFull; f++)
+        for (int i = 0; i < W; i++)
+            for (int j = (f + 1 < kFull ? 1 : 0); j < W; j++) put(mat_g[f][i][j]);
+    for (int j = 0; j < W; j++) put(c4[j]);
+    for (int q = 0; q < kPartial; q++) {
+        put(e_g[q]);
+        for (int j = 0; j < t; j++) put(alpha_g[q][j]);
+        for (int j = 0; j < t; j++) put(crow_g[q][j]);
+    }
     for (int i = 0; i < t; i++)
-        for (int j = 0; j < t; j++) put(Pinv[i][j]);
+        for (int j = 1; j < t; j++) put(pinv_g[i][j]);
     return out.size() == ccf_table_entries(W) * 4;
 }
 

@@ -120,15 +120,26 @@ __global__ void __launch_bounds__(BLOCK, MINB) perm_batch_lockstep_kernel(uint4*
         }
         __syncwarp();
         permute_fast<BlockSync>(s);
-        if (live) {
+        // The indices are RECOMPUTED from the special registers (volatile reads, so they are not merged with
+        // the ones above): nothing but the state is live across the permutation, which keeps the kernel
+        // inside its register budget without a stack slot.
+        unsigned tid2, bid2;
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid2));
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid2));
+        const int lane2 = tid2 & 31;
+        const size_t warp_first2 = (size_t)bid2 * BLOCK + (tid2 & ~31u);
+        const int n_in_warp2 = warp_first2 >= n ? 0 : (n - warp_first2 < 32 ? (int)(n - warp_first2) : 32);
+        uint4* tile2 = stage + (tid2 & ~31u) * kStagePitch;
+        uint4* gbase2 = states + warp_first2 * kChunksPerState;
+        if (lane2 < n_in_warp2) {
 #pragma unroll
-            for (int j = 0; j < W; j++) fr_store(tile + lane * kStagePitch + 2 * j, s[j]);
+            for (int j = 0; j < W; j++) fr_store(tile2 + lane2 * kStagePitch + 2 * j, s[j]);
         }
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < kChunksPerState; k++) {
-            const int c = lane + 32 * k, st = c / kChunksPerState, off = c % kChunksPerState;
-            if (st < n_in_warp) gbase[c] = tile[st * kStagePitch + off];
+            const int c = lane2 + 32 * k, st = c / kChunksPerState, off = c % kChunksPerState;
+            if (st < n_in_warp2) gbase2[c] = tile2[st * kStagePitch + off];
         }
     } else {
         const size_t i = warp_first + lane;
