@@ -38,10 +38,11 @@ WIDTH = 5
 LIMB_PRODUCTS_PER_PERM = 268192   # 1972 Fr mul x 136 (8-limb CIOS), SURVEY.md 8(d)
 # IMAD.WIDE products the kernels actually execute per perm; x^5 = 2*(36+48) + (64+48) = 280,
 # an N-term lazily reduced dot product = 64 N + 48.
-#   default (algo 2, gauged canonical form): partial round 280 + 2 x 4-term dot (304) = 888, x59;
+#   default (algo 2, gauged canonical form): partial round 2*84 (x^2, x^4) + 64 (x^4 * x, unreduced) + 2 x 4-term dot
+#     (304) = 840, x59;
 #     full rounds 0..6: 5*280 + 5*304 = 2920; full round 7 (dense): 5*280 + 5*368 = 3240; P^-1 stage 4 x 3-term dot = 960
 #   algo 1 (sparse partial rounds): partial 280 + 368 + 4 short-reduced b products 4*(64+12) = 952, x59; full 3240, x8
-EXECUTED_PRODUCTS = {2: 59 * 888 + 7 * 2920 + 3240 + 960, 1: 59 * 952 + 8 * 3240}
+EXECUTED_PRODUCTS = {2: 59 * 840 + 7 * 2920 + 3240 + 960, 1: 59 * 952 + 8 * 3240}
 EXECUTED_PRODUCTS_PER_PERM = EXECUTED_PRODUCTS[2]
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE default-kernel launch over 2^26 states, from the
 # `ncu --set full` capture summarised in profiles/r01_ncu_perm5_2p26_final.txt (10.847 + 10.706 GB)

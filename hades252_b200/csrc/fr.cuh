@@ -405,12 +405,22 @@ HADES_DEV void dot_step(uint32_t (&E)[9], uint32_t (&O)[9], uint32_t x, int i, V
 // constants X_j = c * 2^(32*STEPS*(j+1) - 256) mod p are precomputed on the host, so
 //     sum_j X_j * y_j / 2^(32*STEPS)  ==  c * y / 2^256   (mod p)
 // with the same 64 limb products but only 6*STEPS reduction products instead of 48.
-template <int N, int STEPS, class Vec, class Sca>
-HADES_DEV void dot_mont_steps(uint32_t (&r)[9], Vec vec, Sca sca) {
+// With kInject the 16-limb integer `t` is added to the sum before the reduction (STEPS = 8 only):
+//     r = (t + sum_j A_j * B_j) / 2^256.
+// Its low limbs are the initial accumulator contents and each higher limb enters the limb that the
+// one-limb shift has just vacated, so the addition costs no instruction at all (cf. redc16).
+template <int N, int STEPS, bool kInject, class Vec, class Sca>
+HADES_DEV void dot_mont_core(uint32_t (&r)[9], Vec vec, Sca sca, const uint32_t* t) {
     static_assert(STEPS == 2 || STEPS == 4 || STEPS == 8, "even/odd bookkeeping needs an even step count");
+    static_assert(!kInject || STEPS == 8, "the addend is a full 512-bit integer");
     uint32_t A[9], B[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) A[k] = B[k] = 0;
+    if constexpr (kInject) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) A[k] = t[k];
+        B[7] = t[8];  // odd accumulator limb k sits at position k + 1
+    }
     uint32_t x = 0;
 #pragma unroll
     for (int i = 0; i < STEPS; i += 2) {
@@ -421,16 +431,29 @@ HADES_DEV void dot_mont_steps(uint32_t (&r)[9], Vec vec, Sca sca) {
         x = A[1];
 #pragma unroll
         for (int k = 0; k < 7; k++) A[k] = A[k + 2];
-        A[7] = 0; A[8] = 0;
+        A[7] = kInject ? t[i + 9] : 0u;
+        A[8] = 0;
         // step i+1: E = B, O = A
         dot_step<N, false>(B, A, x, i + 1, vec, sca);
         x = B[1];
 #pragma unroll
         for (int k = 0; k < 7; k++) B[k] = B[k + 2];
-        B[7] = 0; B[8] = 0;
+        B[7] = (kInject && i + 10 < 16) ? t[i + 10] : 0u;
+        B[8] = 0;
     }
     // after the steps: E = A (positions 0..8), O = B (positions 1..9), pending x at position 0
     merge_even_odd(r, A, B, x);
+}
+
+template <int N, int STEPS, class Vec, class Sca>
+HADES_DEV void dot_mont_steps(uint32_t (&r)[9], Vec vec, Sca sca) {
+    dot_mont_core<N, STEPS, false>(r, vec, sca, nullptr);
+}
+
+// r = (t + sum_j A_j * B_j) / 2^256 for a 512-bit integer t (one reduction for the sum and the addend)
+template <int N, class Vec, class Sca>
+HADES_DEV void dot_mont_plus(uint32_t (&r)[9], Vec vec, Sca sca, const uint32_t (&t)[16]) {
+    dot_mont_core<N, 8, true>(r, vec, sca, t);
 }
 
 template <int N, class Vec, class Sca>
@@ -513,6 +536,40 @@ HADES_DEV void cmad4r(uint32_t& l0, uint32_t& h0, uint32_t& l1, uint32_t& h1, ui
     uint32_t acc[9] = {l0, h0, l1, h1, l2, h2, l3, h3, land};
     cmad4(acc, a0, a1, a2, a3, b);
     l0 = acc[0]; h0 = acc[1]; l1 = acc[2]; h1 = acc[3]; l2 = acc[4]; h2 = acc[5]; l3 = acc[6]; h3 = acc[7]; land = acc[8];
+}
+
+// t[0..15] = a * b as a plain 512-bit integer (64 products, no reduction).  Two accumulators of 64-bit columns,
+// EA aligned at even limb positions and OA at odd ones (OA[k] = position k + 1); rows in ascending i, so a
+// chain's carry-out always lands in a limb that holds nothing but carries.
+HADES_DEV void mul_wide(uint32_t (&t)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t EA[17], OA[16];
+#pragma unroll
+    for (int k = 0; k < 17; k++) EA[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) OA[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        // b_i, i even: even limbs of a -> positions i + 2k (EA), odd limbs -> positions i + 1 + 2k (OA index i + 2k)
+        cmad4r(EA[i], EA[i + 1], EA[i + 2], EA[i + 3], EA[i + 4], EA[i + 5], EA[i + 6], EA[i + 7], EA[i + 8], a[0], a[2], a[4], a[6], b[i]);
+        cmad4r(OA[i], OA[i + 1], OA[i + 2], OA[i + 3], OA[i + 4], OA[i + 5], OA[i + 6], OA[i + 7], OA[i + 8], a[1], a[3], a[5], a[7], b[i]);
+        // b_{i+1}: even limbs of a -> positions i + 1 + 2k (OA index i + 2k), odd limbs -> positions i + 2 + 2k (EA)
+        cmad4r(OA[i], OA[i + 1], OA[i + 2], OA[i + 3], OA[i + 4], OA[i + 5], OA[i + 6], OA[i + 7], OA[i + 8], a[0], a[2], a[4], a[6], b[i + 1]);
+        cmad4r(EA[i + 2], EA[i + 3], EA[i + 4], EA[i + 5], EA[i + 6], EA[i + 7], EA[i + 8], EA[i + 9], EA[i + 10], a[1], a[3], a[5], a[7], b[i + 1]);
+    }
+    uint32_t lo[8], hi[8], e_lo[8], e_hi[8], o_lo[8], o_hi[8];
+    o_lo[0] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) e_lo[k] = EA[k];
+#pragma unroll
+    for (int k = 1; k < 8; k++) o_lo[k] = OA[k - 1];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { e_hi[k] = EA[8 + k]; o_hi[k] = OA[7 + k]; }
+    uint32_t c = add8(lo, e_lo, o_lo);
+    uint32_t c2 = add8_cin(hi, e_hi, o_hi, c);
+    HADES_ASSERT(c2 == 0 && EA[16] == 0 && OA[15] == 0);  // a * b < 2^512
+    (void)c2;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { t[k] = lo[k]; t[8 + k] = hi[k]; }
 }
 
 // t[0..15] = 2*t + sum_i a_i^2 * 2^(64 i)   (t < 2^511 on entry; the result a^2-part fits 512 bits)

@@ -280,7 +280,8 @@ HADES_DEV void hades_perm_opt(Fr (&s)[W]) {
 // Canonical-form schedule with a diagonal gauge (algo 2; derivation in host_tables.hpp, derive_tables_ccf).
 // Every word is kept multiplied by a host-chosen scalar so that one matrix entry per output row is 1:
 //   full rounds 0..6:   row_i = s_0 + sum_{j>=1} M^_f[i][j] s_j          (W-1 products per row)
-//   partial round q:    x += e_q ; y = x^5 ; w_t' = alpha_q . w + y ; x' = c_q . w + y ; w_i' = w_{i+1}
+//   partial round q:    x += e_q ; y = x^4 * x (512 bits) ; w_t' = (alpha_q . w + y) / R ; x' = (c_q . w + y) / R ;
+//                       w_i' = w_{i+1}
 //   P^-1 stage:         z_i = w_0 + sum_{j>=1} Q[i][j] w_j
 //   full round 7:       dense (removes the gauge)
 // ------------------------------------------------------------------------------------------------
@@ -356,23 +357,24 @@ HADES_DEV void partial_round_ccf(Fr (&s)[W], int base) {
         for (int k = 0; k < 8; k++) e.l[k] = T::tab(base, k);
         fr_add(s[t], s[t], e);
     }
-    Fr y, x4;
+    // y = x^4 * x is NOT reduced on its own: the 512-bit product enters both dot products below as an addend
+    // and shares their reductions (the gauge made its coefficient 1 in both).
+    // Bound: (sum_{j<t} c_j w_j + x^4 x) / R + p  <  p (1 + 0.4528 (t + 1.956)):  W=3: 2.8p, W=5: 3.7p, W=9: 5.6p
+    Fr x4;
     fr_pow4_lazy(x4, s[t]);
-    fr_mul(y, x4, s[t]);  // canonical: it is added to both dot products below
-    // both new words: (t-term dot) + y  <  (1 + 0.4528 t) p + p
+    uint32_t y[16];
+    mul_wide(y, x4.l, s[t].l);
     Fr newx, neww;
     {
         uint32_t r[9];
-        dot_mont<t>(
-            r, [&](int j, int k) { return T::tab(base + 1 + t + j, k); }, [&](int j, int i) { return s[j].l[i]; });
-        add_into9(r, y);
+        dot_mont_plus<t>(
+            r, [&](int j, int k) { return T::tab(base + 1 + t + j, k); }, [&](int j, int i) { return s[j].l[i]; }, y);
         canon<(W <= 5) ? 1 : 2>(newx, r);
     }
     {
         uint32_t r[9];
-        dot_mont<t>(
-            r, [&](int j, int k) { return T::tab(base + 1 + j, k); }, [&](int j, int i) { return s[j].l[i]; });
-        add_into9(r, y);
+        dot_mont_plus<t>(
+            r, [&](int j, int k) { return T::tab(base + 1 + j, k); }, [&](int j, int i) { return s[j].l[i]; }, y);
         canon<(W <= 5) ? 1 : 2>(neww, r);
     }
     // shift the words, the new one enters at the end
