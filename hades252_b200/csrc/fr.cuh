@@ -59,17 +59,37 @@ struct Fr {
 // Deliberately NOT statically initialised (an initialiser gets folded back into immediates): every
 // translation unit that multiplies by the modulus uploads it once with upload_modulus().
 #if !HADES_EMUL
-static __constant__ uint32_t c_modp[8];
+static __constant__ uint32_t c_modp[9];  // p[0..7], then a zero the compiler cannot see (mont_quotient)
 HADES_DEV uint32_t modp(int k) { return c_modp[k]; }
 #if defined(__CUDACC__)
 static inline cudaError_t upload_modulus() {
-    const uint32_t p[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    const uint32_t p[9] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u, 0u};
     return cudaMemcpyToSymbol(c_modp, p, sizeof(p), 0, cudaMemcpyHostToDevice);
 }
 #endif
 #else
 HADES_DEV uint32_t modp(int k) { return p_limb(k); }
 #endif
+
+// Montgomery quotient of one reduction step: m = -t0 mod 2^32 (because -p^-1 = -1 mod 2^32), and
+// nz = (t0 != 0) = the carry of t0 + m.  m is computed as  c - t0  with c a zero read from constant memory:
+// if ptxas can prove m == -t0 it rewrites every m*p[k] product into IMAD.X + IMAD.HI.U32.X pairs (7.1 pipe
+// cycles instead of 4.05).  Three ALU instructions per step: m, nz, m - nz.
+struct MontQ {
+    uint32_t t0, m, nz, mm;
+};
+HADES_DEV MontQ mont_quotient(uint32_t t0) {
+    MontQ q;
+    q.t0 = t0;
+    q.m = modp(8) - t0;
+#if !HADES_EMUL
+    asm("min.u32 %0, %1, 1;" : "=r"(q.nz) : "r"(t0));  // one VIMNMX (a ternary compiles to ISETP + SEL)
+#else
+    q.nz = t0 ? 1u : 0u;
+#endif
+    q.mm = q.m - q.nz;
+    return q;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Chain primitives.  Each is ONE asm statement: the carry flag never lives across statements.
@@ -145,28 +165,25 @@ HADES_DEV void cmad4_shiftin(uint32_t (&acc)[9], uint32_t a0, uint32_t a1, uint3
 // Montgomery step on the accumulator that owns limb 0.  With m = -acc[0] mod 2^32:
 //   acc += m * (p0 + p2*2^64 + p4*2^128 + p6*2^192);  p0 = 1 so limb 0 becomes 0 and only its
 //   carry (acc[0] != 0) matters.  3 products.  (The odd limbs p1,p3,p5,p7 go through cmad4.)
-HADES_DEV void redc_even(uint32_t (&acc)[9], uint32_t m) {
+HADES_DEV void redc_even(uint32_t (&acc)[9], const MontQ& q) {
+    // limb 0 (t0 + m = nz * 2^32) is not written: the caller drops it with the next shift
 #if !HADES_EMUL
-    asm("add.cc.u32 %0, %0, %9;\n\t"
-        "addc.cc.u32 %1, %1, 0;\n\t"
-        "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
-        "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
-        "madc.lo.cc.u32 %4, %9, %11, %4;\n\t"
-        "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
-        "madc.lo.cc.u32 %6, %9, %12, %6;\n\t"
-        "madc.hi.cc.u32 %7, %9, %12, %7;\n\t"
-        "addc.u32 %8, %8, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
-          "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
-        : "r"(m), "r"(modp(2)), "r"(modp(4)), "r"(modp(6)));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %2;\n\t"
+        "madc.lo.cc.u32 %3, %9, %11, %3;\n\t"
+        "madc.hi.cc.u32 %4, %9, %11, %4;\n\t"
+        "madc.lo.cc.u32 %5, %9, %12, %5;\n\t"
+        "madc.hi.cc.u32 %6, %9, %12, %6;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(q.nz), "r"(q.m), "r"(modp(2)), "r"(modp(4)), "r"(modp(6)));
 #else
-    uint64_t s = (uint64_t)acc[0] + m;
-    acc[0] = (uint32_t)s;
-    HADES_ASSERT(acc[0] == 0);
-    s = (uint64_t)acc[1] + (s >> 32);
+    HADES_ASSERT((uint32_t)(acc[0] + q.m) == 0 && q.nz >= (acc[0] != 0 ? 1u : 0u) && q.nz <= 2u);
+    uint64_t s = (uint64_t)acc[1] + q.nz;
     acc[1] = (uint32_t)s;
     const uint32_t a[4] = {0, p_limb(2), p_limb(4), p_limb(6)};
-    emul::top(acc[8], emul::chain(acc, a, 1, m, s >> 32));
+    emul::top(acc[8], emul::chain(acc, a, 1, q.m, s >> 32));
 #endif
 }
 
@@ -175,9 +192,8 @@ HADES_DEV void redc_even(uint32_t (&acc)[9], uint32_t m) {
 //   t0 + m*(p0 + p1*2^32) = nz*2^32 + t0*2^32 + (m - nz)*2^64
 // i.e. m*p[1] needs no product: position 1 gets +t0 (the +nz is the carry of even[0] + m, already
 // added by redc_even) and position 2 gets +(m - nz).  3 products (p3, p5, p7) instead of 4.
-HADES_DEV void redc_odd(uint32_t (&acc)[9], uint32_t t0, uint32_t m) {
-    // m - nz without a branch: m == 0 iff t0 == 0
-    uint32_t mm = (m > 1u ? m : 1u) - 1u;
+HADES_DEV void redc_odd(uint32_t (&acc)[9], const MontQ& q) {
+    const uint32_t t0 = q.t0, mm = q.mm, m = q.m;
 #if !HADES_EMUL
     asm("add.cc.u32 %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, %10;\n\t"
@@ -389,22 +405,12 @@ HADES_DEV void dot_step(uint32_t (&E)[9], uint32_t (&O)[9], uint32_t x, int i, V
     // even limbs -> E (positions 0..7)
 #pragma unroll
     for (int j = 0; j < N; j++) cmad4(E, vec(j, 0), vec(j, 2), vec(j, 4), vec(j, 6), sca(j, i));
-    // Montgomery step: m = -E[0] (since -p^-1 = -1 mod 2^32); add m*p so that position 0 clears.
-    // Written as (E0 ^ p[1]) + p[0] = ~E0 + 1 with the two limbs read from constant memory: if ptxas
-    // can prove m == -E0 it rewrites every m*p[k] product into IMAD.X + IMAD.HI.U32.X pairs
-    // (7.1 pipe cycles instead of 4.05).
-    uint32_t t0 = E[0];
-    uint32_t m = (t0 ^ modp(1)) + modp(0);
-    redc_odd(O, t0, m);
-    redc_even(E, m);
+    // Montgomery step: add m*p so that position 0 clears
+    const MontQ q = mont_quotient(E[0]);
+    redc_odd(O, q);
+    redc_even(E, q);
 }
 
-// STEPS outer steps (even): r = (sum_j A_j * B_j[0..STEPS)) / 2^(32*STEPS), where B_j is consumed
-// STEPS limbs deep.  STEPS = 8 is the ordinary Montgomery product (R = 2^256).  Smaller STEPS implement
-// the SHORT reduction used for multiplications by constants: y = sum_j y_j 2^(32*STEPS*j) and the
-// constants X_j = c * 2^(32*STEPS*(j+1) - 256) mod p are precomputed on the host, so
-//     sum_j X_j * y_j / 2^(32*STEPS)  ==  c * y / 2^256   (mod p)
-// with the same 64 limb products but only 6*STEPS reduction products instead of 48.
 // With kInject the 16-limb integer `t` is added to the sum before the reduction (STEPS = 8 only):
 //     r = (t + sum_j A_j * B_j) / 2^256.
 // Its low limbs are the initial accumulator contents and each higher limb enters the limb that the
@@ -630,32 +636,6 @@ HADES_DEV uint32_t add_carry_out(uint32_t& e0, uint32_t x) {
     return c;
 }
 
-// redc_even with an extra carry `cx` (0/1) entering limb 1
-HADES_DEV void redc_even_c(uint32_t (&acc)[9], uint32_t m, uint32_t cx) {
-#if !HADES_EMUL
-    asm("add.cc.u32 %0, %0, %9;\n\t"
-        "addc.cc.u32 %1, %1, %13;\n\t"
-        "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
-        "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
-        "madc.lo.cc.u32 %4, %9, %11, %4;\n\t"
-        "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
-        "madc.lo.cc.u32 %6, %9, %12, %6;\n\t"
-        "madc.hi.cc.u32 %7, %9, %12, %7;\n\t"
-        "addc.u32 %8, %8, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
-          "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
-        : "r"(m), "r"(modp(2)), "r"(modp(4)), "r"(modp(6)), "r"(cx));
-#else
-    uint64_t s = (uint64_t)acc[0] + m;
-    acc[0] = (uint32_t)s;
-    HADES_ASSERT(acc[0] == 0);
-    s = (uint64_t)acc[1] + cx + (s >> 32);
-    acc[1] = (uint32_t)s;
-    const uint32_t a[4] = {0, p_limb(2), p_limb(4), p_limb(6)};
-    emul::top(acc[8], emul::chain(acc, a, 1, m, s >> 32));
-#endif
-}
-
 // r = t / 2^256 mod p (9 limbs, < t/2^256 + p) for a merged 512-bit t: the reduce-only version of
 // dot_mont -- same even/odd bookkeeping, the upper limbs of t are injected one per shift.
 HADES_DEV void redc16(uint32_t (&r)[9], const uint32_t (&t)[16]) {
@@ -669,10 +649,10 @@ HADES_DEV void redc16(uint32_t (&r)[9], const uint32_t (&t)[16]) {
     for (int i = 0; i < 8; i += 2) {
         {  // step i: E = A, O = B
             uint32_t cx = (i == 0) ? 0u : add_carry_out(A[0], x);
-            uint32_t t0 = A[0];
-            uint32_t m = (t0 ^ modp(1)) + modp(0);
-            redc_odd(B, t0, m);
-            redc_even_c(A, m, cx);
+            MontQ q = mont_quotient(A[0]);
+            redc_odd(B, q);
+            q.nz += cx;  // both carries enter limb 1
+            redc_even(A, q);
             x = A[1];
 #pragma unroll
             for (int k = 0; k < 7; k++) A[k] = A[k + 2];
@@ -681,10 +661,10 @@ HADES_DEV void redc16(uint32_t (&r)[9], const uint32_t (&t)[16]) {
         }
         {  // step i+1: E = B, O = A
             uint32_t cx = add_carry_out(B[0], x);
-            uint32_t t0 = B[0];
-            uint32_t m = (t0 ^ modp(1)) + modp(0);
-            redc_odd(A, t0, m);
-            redc_even_c(B, m, cx);
+            MontQ q = mont_quotient(B[0]);
+            redc_odd(A, q);
+            q.nz += cx;
+            redc_even(B, q);
             x = B[1];
 #pragma unroll
             for (int k = 0; k < 7; k++) B[k] = B[k + 2];

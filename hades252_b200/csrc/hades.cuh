@@ -138,6 +138,9 @@ HADES_DEV void add_table_vector(Fr (&s)[W], int base) {
 #define HADES_NO_UNROLL _Pragma("unroll 1")
 #endif
 
+#ifndef HADES_SYNC_PERIOD
+#define HADES_SYNC_PERIOD 1  // block barrier every this many partial rounds (lockstep kernels; tuning knob)
+#endif
 struct NoSync {
     static HADES_DEV void sync() {}
 };
@@ -403,7 +406,11 @@ HADES_DEV void hades_perm_ccf(Fr (&s)[W]) {
 #endif
             for (int q = 0; q < kPartialRounds; q++) {
                 partial_round_ccf<W, T>(s, L::kPart + q * L::kPartStride);
+#if HADES_SYNC_PERIOD > 1
+                if (q % HADES_SYNC_PERIOD == HADES_SYNC_PERIOD - 1) Sync::sync();
+#else
                 Sync::sync();
+#endif
             }
             // back to the original basis (gauged): z_i = w_0 + sum_{j>=1} Q[i][j] w_j ; the last word stays
             Fr w[t];

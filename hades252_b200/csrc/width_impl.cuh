@@ -219,7 +219,12 @@ merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ o
         else fr_set_zero(s[1 + j]);
     }
     permute_fast<BlockSync>(s);
-    if (live) fr_store(out + (warp_first + lane) * 2, s[1]);
+    // indices recomputed from the special registers (see perm_batch_lockstep_kernel): no stack slot
+    unsigned tid2, bid2;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid2));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid2));
+    const size_t node = (size_t)bid2 * BLOCK + tid2;
+    if (node < n_out) fr_store(out + node * 2, s[1]);
 }
 #endif  // HADES_ALGO >= 1
 
