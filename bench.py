@@ -203,6 +203,29 @@ def _bind_to_gpu_cpus(index: int):
         return f"unbound ({type(e).__name__})"
 
 
+def _prefer_gpu_numa_node(index: int):
+    """Ask the kernel to place this rank's future allocations (the pinned host buffers of the e2e leg) on the
+    NUMA node its GPU hangs off: set_mempolicy(MPOL_PREFERRED, node).  With 8 ranks the copies otherwise all
+    cross one socket's memory controller and the inter-socket link.  Best effort; returns the node or a reason."""
+    try:
+        import ctypes
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "single node"
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL(None, use_errno=True)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238  # x86_64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+        return node if rc == 0 else f"set_mempolicy errno {ctypes.get_errno()}"
+    except Exception as e:  # noqa: BLE001
+        return f"unset ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import numpy as np
@@ -216,6 +239,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     numa = _bind_to_gpu_cpus(local)
+    numa_node = _prefer_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -234,10 +258,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # roofline denominator, measured live on this device
-    peaks = {v: strat.imad_peak(v) for v in range(4)}
-    names = {0: "imad_wide_x_carry_chain", 1: "imad_wide_carry_out_only", 2: "imad_lo32_half_product_context_only",
-             3: "imad_lo_plus_imad_hi_pair"}
-    p_mul32 = max(peaks[0], peaks[1], peaks[3])  # forms that deliver a full 64-bit multiply-accumulate
+    peaks = {v: strat.imad_peak(v) for v in range(5)}
+    names = {0: "imad_wide_x_carry_chain4", 1: "imad_wide_carry_out_only", 2: "imad_lo32_half_product_context_only",
+             3: "imad_lo_plus_imad_hi_pair", 4: "imad_wide_x_carry_chain16"}
+    p_mul32 = max(peaks[0], peaks[1], peaks[3], peaks[4])  # forms that deliver a full 64-bit multiply-accumulate
     info = strat.kernel_info("perm")
 
     # ---- device-resident leg: states generated on device, permuted in place K times -------------
@@ -326,7 +350,7 @@ def run_ours(args):
                "h2d_bytes_per_step": ne * HBM_BYTES_PER_PERM // 2 * world, "d2h_bytes_per_step": ne * HBM_BYTES_PER_PERM // 2 * world,
                "states_per_gpu_per_step": ne, "steps": e2e_steps, "host_memory": "pinned",
                "api": "hades_perm_batch (C ABI, chunked H2D/kernel/D2H pipeline)", "gpu_launches": e2e_launches,
-               "cpu_affinity": numa}
+               "cpu_affinity": numa, "numa_node_rank0": numa_node}
         del host
 
     cpu_baseline = None

@@ -528,7 +528,7 @@ int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uin
 }
 
 int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products_per_s) {
-    if (!valid_dev(ctx, dev_index) || !products_per_s || variant < 0 || variant > 3)
+    if (!valid_dev(ctx, dev_index) || !products_per_s || variant < 0 || variant > 4)
         return fail(ctx, HADES_ERR_INVALID_ARG, "bad argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     const int threads = 256, blocks = 148 * 8;
@@ -546,6 +546,7 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
             case 0: imad_peak_kernel<0><<<blocks, threads>>>(d_in, d_out, iters); break;
             case 1: imad_peak_kernel<1><<<blocks, threads>>>(d_in, d_out, iters); break;
             case 2: imad_peak_kernel<2><<<blocks, threads>>>(d_in, d_out, iters); break;
+            case 4: imad_peak_kernel<4><<<blocks, threads>>>(d_in, d_out, iters); break;
             default: imad_peak_kernel<3><<<blocks, threads>>>(d_in, d_out, iters); break;
         }
         ctx->launches++;
@@ -561,7 +562,7 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
         CUDA_TRY(ctx, cudaEventSynchronize(e1));
         float ms = 0;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
-        double prods = (double)threads * blocks * (double)iters * (variant == 0 ? kPeakProductsPerIterV0 : kPeakProductsPerIterV123);
+        double prods = (double)threads * blocks * (double)iters * (variant == 0 ? kPeakProductsPerIterV0 : variant == 4 ? kPeakProductsPerIterV4 : kPeakProductsPerIterV123);
         best = std::max(best, prods / (ms * 1e-3));
     }
     CUDA_TRY(ctx, cudaGetLastError());

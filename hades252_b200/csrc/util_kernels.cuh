@@ -64,6 +64,47 @@ __global__ void sponge_keys_kernel(const uint64_t* __restrict__ offsets, uint32_
 //   variant 1: IMAD.WIDE.U32 with carry-out only + IADD3.X;                                      P = 1
 //   variant 2: IMAD (32-bit low half only -- NOT a full product, context only);                  P = 1
 //   variant 3: IMAD + IMAD.HI.U32 pair per product;                                              P = 1
+//   variant 4: 16-link carry chains, 4 independent accumulators (products per iteration 8*4*16)
+// 16-link carry chain (one landing add per 16 products): the closest a program gets to the bare pipe rate
+__device__ __forceinline__ void cmad16(uint32_t (&acc)[33], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    asm(
+        "mad.lo.cc.u32 %0, %33, %37, %0;\n\t"
+        "madc.hi.cc.u32 %1, %33, %37, %1;\n\t"
+        "madc.lo.cc.u32 %2, %34, %37, %2;\n\t"
+        "madc.hi.cc.u32 %3, %34, %37, %3;\n\t"
+        "madc.lo.cc.u32 %4, %35, %37, %4;\n\t"
+        "madc.hi.cc.u32 %5, %35, %37, %5;\n\t"
+        "madc.lo.cc.u32 %6, %36, %37, %6;\n\t"
+        "madc.hi.cc.u32 %7, %36, %37, %7;\n\t"
+        "madc.lo.cc.u32 %8, %33, %37, %8;\n\t"
+        "madc.hi.cc.u32 %9, %33, %37, %9;\n\t"
+        "madc.lo.cc.u32 %10, %34, %37, %10;\n\t"
+        "madc.hi.cc.u32 %11, %34, %37, %11;\n\t"
+        "madc.lo.cc.u32 %12, %35, %37, %12;\n\t"
+        "madc.hi.cc.u32 %13, %35, %37, %13;\n\t"
+        "madc.lo.cc.u32 %14, %36, %37, %14;\n\t"
+        "madc.hi.cc.u32 %15, %36, %37, %15;\n\t"
+        "madc.lo.cc.u32 %16, %33, %37, %16;\n\t"
+        "madc.hi.cc.u32 %17, %33, %37, %17;\n\t"
+        "madc.lo.cc.u32 %18, %34, %37, %18;\n\t"
+        "madc.hi.cc.u32 %19, %34, %37, %19;\n\t"
+        "madc.lo.cc.u32 %20, %35, %37, %20;\n\t"
+        "madc.hi.cc.u32 %21, %35, %37, %21;\n\t"
+        "madc.lo.cc.u32 %22, %36, %37, %22;\n\t"
+        "madc.hi.cc.u32 %23, %36, %37, %23;\n\t"
+        "madc.lo.cc.u32 %24, %33, %37, %24;\n\t"
+        "madc.hi.cc.u32 %25, %33, %37, %25;\n\t"
+        "madc.lo.cc.u32 %26, %34, %37, %26;\n\t"
+        "madc.hi.cc.u32 %27, %34, %37, %27;\n\t"
+        "madc.lo.cc.u32 %28, %35, %37, %28;\n\t"
+        "madc.hi.cc.u32 %29, %35, %37, %29;\n\t"
+        "madc.lo.cc.u32 %30, %36, %37, %30;\n\t"
+        "madc.hi.cc.u32 %31, %36, %37, %31;\n\t"
+        "addc.u32 %32, %32, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(acc[14]), "+r"(acc[15]), "+r"(acc[16]), "+r"(acc[17]), "+r"(acc[18]), "+r"(acc[19]), "+r"(acc[20]), "+r"(acc[21]), "+r"(acc[22]), "+r"(acc[23]), "+r"(acc[24]), "+r"(acc[25]), "+r"(acc[26]), "+r"(acc[27]), "+r"(acc[28]), "+r"(acc[29]), "+r"(acc[30]), "+r"(acc[31]), "+r"(acc[32])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
 constexpr int kPeakIlp = 8;
 template <int VARIANT>
 __global__ void __launch_bounds__(256) imad_peak_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
@@ -87,6 +128,23 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(const uint32_t* __restri
         for (int k = 0; k < kPeakIlp; k++)
 #pragma unroll
             for (int q = 0; q < 9; q++) r ^= e[k][q];
+    } else if (VARIANT == 4) {
+        uint32_t e[4][33];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int q = 0; q < 33; q++) e[k][q] = my[(k + q) & 31];
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) cmad16(e[k], a, b, a ^ 0x5555u, b ^ 0x3333u, e[(k + 1) & 3][1]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int q = 0; q < 33; q++) r ^= e[k][q];
     } else if (VARIANT == 1) {
         uint32_t lo[kPeakIlp], hi[kPeakIlp], t[kPeakIlp];
 #pragma unroll
@@ -136,5 +194,6 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(const uint32_t* __restri
 }
 constexpr double kPeakProductsPerIterV0 = 8.0 * 8.0 * 4.0;
 constexpr double kPeakProductsPerIterV123 = 8.0 * 8.0;
+constexpr double kPeakProductsPerIterV4 = 8.0 * 4.0 * 16.0;
 
 }  // namespace hades

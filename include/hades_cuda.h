@@ -133,7 +133,8 @@ int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uin
 /* Integer-multiply roofline microbenchmark on devices[dev_index]: 32x32->64 multiply-accumulates per
  * second.  variant 0: IMAD.WIDE.U32.X carry chains (the production idiom); 1: IMAD.WIDE.U32 with
  * carry-out only; 2: IMAD 32-bit low half only (context: not a full product); 3: IMAD + IMAD.HI.U32
- * pair per product.  Instruction forms validated in tools/microbench.cu. */
+ * pair per product; 4: 16-link carry chains (one landing add per 16 products: the bare pipe rate).
+ * Instruction forms validated in tools/microbench.cu. */
 int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products_per_s);
 /* Registers per thread / local (spill) bytes / max threads per block of the context's current kernel
  * variant: kernel = "perm" | "merkle" | "sponge" (the last two for width 5). */
