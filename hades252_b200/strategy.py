@@ -172,8 +172,9 @@ class CudaStrategy(Strategy):
                                                 ctypes.byref(thr)))
         return {"regs_per_thread": regs.value, "local_bytes": local.value, "max_threads_per_block": thr.value}
 
-    def set_variant(self, algo: int = 1, regs: int = 0) -> None:
-        """Kernel variant (bit-identical results): algo 0 dense / 1 sparse partial rounds; regs 0 <=128, 1 <=168."""
+    def set_variant(self, algo: int = 2, regs: int = 6) -> None:
+        """Kernel variant (bit-identical results): algo 0 dense / 1 sparse partial rounds / 2 gauged canonical form
+        (default); regs = launch shape (include/hades_cuda.h; 6 = lockstep 128-thread blocks, the default at W = 3, 5)."""
         self._check(self._lib.hades_set_variant(self._ctx, algo, regs))
 
     def host_register(self, ptr: int, nbytes: int) -> None:

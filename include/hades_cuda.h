@@ -141,7 +141,8 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
 int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
                       int* max_threads_per_block);
 /* Select the kernel variant (all bit-identical): algo 0 = dense schedule (the reference's round
- * structure), 1 = optimised schedule (sparse partial rounds; default), 2 = canonical-form schedule; launch shape `regs`: 0/1/2/3 = 128-thread blocks
+ * structure), 1 = sparse partial rounds, 2 = gauged canonical-form schedule (default; HADES_ERR_CONSTANTS if it
+ * could not be derived for the context's constants); launch shape `regs`: 0/1/2/3 = 128-thread blocks
  * with at most 128/168/255/96 registers per thread, 4/5 = lockstep blocks of 256/512 threads, 6.. = lockstep
  * 128-thread blocks (the default; see hades252_b200/csrc/width_ops.hpp). */
 int hades_set_variant(hades_ctx* ctx, int algo, int regs);

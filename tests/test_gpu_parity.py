@@ -419,3 +419,46 @@ def test_generic_width_kernel(oracle, w):
         with pytest.raises(HadesError):
             strat.set_variant(0, 0)
         assert strat.kernel_info("perm")["regs_per_thread"] > 0
+
+
+_CUSTOM_CONSTANTS_SCRIPT = r"""
+import ctypes, sys
+import numpy as np
+from hades252_b200 import _native
+from oracle import cpu_oracle as C
+
+w = int(sys.argv[1])
+L, O = _native.lib(), C.lib()
+ark = C.gen_elems(4242, 960)                 # random round constants (< 2^254 < p, Montgomery limbs)
+mds = C.gen_elems(777 + w, w * w)            # random dense matrix instead of the Cauchy MDS
+n = 1500
+states = C.gen_elems(99, w * n).reshape(n, w, 4)
+want = states.copy()
+p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+assert O.oracle_perm_batch(p(want), n, w, p(ark), p(mds), 4) == 0
+ctx = _native.ctx_p()
+dev = (ctypes.c_int * 1)(0)
+rc = L.hades_init(ctypes.byref(ctx), dev, 1, w, p(ark), 960, p(mds))
+assert rc == 0, L.hades_last_error(None)
+for algo in (2, 1, 0):
+    assert L.hades_set_variant(ctx, algo, 0) == 0, L.hades_last_error(ctx)
+    got = states.copy()
+    assert L.hades_perm_batch(ctx, got.ctypes.data_as(ctypes.c_void_p), n) == 0, L.hades_last_error(ctx)
+    assert np.array_equal(got, want), f"algo {algo} differs from the oracle with custom constants"
+L.hades_destroy(ctx)
+print("custom constants OK")
+"""
+
+
+@pytest.mark.parametrize("w", [3, 5, 9])
+def test_custom_constants_all_schedules(w):
+    """hades_init with RANDOM round constants and a RANDOM dense matrix (own process: the constant tables are
+    process-wide per device, like the crate's consts): the host-side derivations of the sparse and the gauged
+    canonical-form schedules are generic, so every schedule must match the oracle run with the same tables."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", _CUSTOM_CONSTANTS_SCRIPT, str(w)], cwd=root, capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and "custom constants OK" in res.stdout, res.stdout + res.stderr

@@ -22,3 +22,20 @@ def test_host_emulation_bit_exact(tmp_path):
     res = subprocess.run([os.path.join(d, "emul_main"), str(tables)], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "host emulation OK" in res.stdout
+
+
+def test_host_emulation_random_constants(tmp_path):
+    """Same emulation with RANDOM round constants and RANDOM (dense, non-Cauchy) matrices for W = 3, 5, 9: the
+    host-side table derivations (sparse factorisation, controller canonical form, diagonal gauge) are generic
+    linear algebra over F_p, so all three schedules must still equal the reference round structure bit for bit."""
+    d = os.path.join(HERE, "host_emul")
+    subprocess.check_call(["make", "-C", d, "emul_main"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for seed in (11, 12):
+        tables = tmp_path / f"tables_{seed}.bin"
+        with open(tables, "wb") as f:
+            f.write(C.gen_elems(1000 * seed, 960).tobytes())
+            for w in (3, 5, 9):
+                f.write(C.gen_elems(1000 * seed + w, w * w).tobytes())
+        res = subprocess.run([os.path.join(d, "emul_main"), str(tables)], capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert "host emulation OK" in res.stdout
