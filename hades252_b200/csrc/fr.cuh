@@ -16,8 +16,12 @@
 //  * word-serial Montgomery reduction interleaved with the products (CIOS), generalised to an
 //    N-term dot product  sum_j c_j*v_j  that is reduced ONCE (lazy reduction of an MDS row);
 //  * special modulus: p[0] = 1 and -p^{-1} mod 2^32 = 0xffffffff, so the Montgomery quotient is
-//    m = -t0 (no multiply); m*p[0] and m*p[1] (p[1] = 2^32 - 1) need no product: 6 products per
-//    reduction step, the rest is two adds on the ALU pipe.
+//    m = -t0 (no multiply); m*p[0] and m*p[1] (p[1] = 2^32 - 1) need no product: 6 products and 8
+//    ALU instructions per reduction step (mont_quotient, redc_odd, redc_even);
+//  * a 512-bit addend can share a dot product's reduction at no cost (dot_mont_plus), which lets the
+//    partial rounds keep the S-box output x^4 * x as an unreduced product (mul_wide).
+//  Cost model measured on B200: 4.0 cycles per IMAD.WIDE and ~0.63 per other
+//  instruction per SM sub-partition -- ALU instructions are not free beside the multiply pipe.
 //
 // The same source compiles with g++ -DHADES_HOST_EMUL (tests/host_emul): the PTX chains are then
 // replaced by portable C++ of identical semantics, so the limb-level algorithm is checked against
@@ -245,7 +249,7 @@ HADES_DEV void merge_even_odd(uint32_t (&r)[9], const uint32_t (&e)[9], const ui
 }
 
 // (a[0..7], a8 as limb 8) - (p << S) over 9 limbs; difference (low 8 limbs) in d, limb 8 of the
-// difference in d8; returns 1 if the value was below p << S (final borrow).
+// difference in d8; returns an all-ones MASK if the value was below p << S (final borrow), else 0.
 template <int S>
 HADES_DEV uint32_t sub_p_shl(uint32_t (&d)[8], uint32_t& d8, const uint32_t (&a)[8], uint32_t a8) {
     uint32_t below;
@@ -268,7 +272,7 @@ HADES_DEV uint32_t sub_p_shl(uint32_t (&d)[8], uint32_t& d8, const uint32_t (&a)
           "r"(p_shl_limb(S, 4)), "r"(p_shl_limb(S, 5)), "r"(p_shl_limb(S, 6)), "r"(p_shl_limb(S, 7)),
           "r"(p_shl_limb(S, 8)));
     d8 = t8;
-    below = t9 & 1u;  // 0 - 0 - borrow
+    below = t9;  // 0 - 0 - borrow: 0 or 0xffffffff
 #else
     uint64_t bw = 0;
     for (int k = 0; k < 8; k++) {
@@ -278,10 +282,43 @@ HADES_DEV uint32_t sub_p_shl(uint32_t (&d)[8], uint32_t& d8, const uint32_t (&a)
     }
     uint64_t t = (uint64_t)a8 - p_shl_limb(S, 8) - bw;
     d8 = (uint32_t)t;
-    below = (uint32_t)((t >> 63) & 1);
+    below = ((t >> 63) & 1) ? 0xffffffffu : 0u;
 #endif
     return below;
 }
+
+// 8-limb version for values known to be below 2^256 and S = 0 (p itself): the 9th limb is skipped
+HADES_DEV uint32_t sub_p8(uint32_t (&d)[8], const uint32_t (&a)[8]) {
+    uint32_t below;
+#if !HADES_EMUL
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(below)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(p_limb(0)), "r"(p_limb(1)), "r"(p_limb(2)), "r"(p_limb(3)), "r"(p_limb(4)), "r"(p_limb(5)), "r"(p_limb(6)),
+          "r"(p_limb(7)));
+#else
+    uint64_t bw = 0;
+    for (int k = 0; k < 8; k++) {
+        uint64_t t = (uint64_t)a[k] - p_limb(k) - bw;
+        d[k] = (uint32_t)t;
+        bw = (t >> 63) & 1;
+    }
+    below = bw ? 0xffffffffu : 0u;
+#endif
+    return below;
+}
+
+// mask ? a : b per bit (one LOP3): the conditional subtractions select with the borrow MASK, which saves
+// turning the borrow into a predicate (LOP3 + ISETP per subtraction)
+HADES_DEV uint32_t bitsel(uint32_t mask, uint32_t a, uint32_t b) { return b ^ ((a ^ b) & mask); }
 
 // r = a + b over 8 limbs, returns the carry-out limb (0/1).
 HADES_DEV uint32_t add8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
@@ -309,6 +346,27 @@ HADES_DEV uint32_t add8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t
     carry = (uint32_t)(s >> 32);
 #endif
     return carry;
+}
+
+// r = a + b over 8 limbs for sums known to stay below 2^256 (no carry-out instruction)
+HADES_DEV void add8_nc(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#if !HADES_EMUL
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint32_t c = add8(r, a, b);
+    HADES_ASSERT(c == 0);
+    (void)c;
+#endif
 }
 
 // r = a + b + cin (cin = 0/1) over 8 limbs, returns the carry-out limb (0/1).
@@ -349,8 +407,15 @@ HADES_DEV void cond_sub_p_shl(uint32_t (&x)[8], uint32_t& x8) {
     uint32_t d[8], d8;
     uint32_t below = sub_p_shl<S>(d, d8, x, x8);
 #pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = below ? x[k] : d[k];
-    x8 = below ? x8 : d8;
+    for (int k = 0; k < 8; k++) x[k] = bitsel(below, x[k], d[k]);
+    x8 = bitsel(below, x8, d8);
+}
+// x -> x - p if that is non-negative, for x < 2^256
+HADES_DEV void cond_sub_p8(uint32_t (&x)[8]) {
+    uint32_t d[8];
+    uint32_t below = sub_p8(d, x);
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = bitsel(below, x[k], d[k]);
 }
 
 // r (9 limbs, value < 2^(LOG2+1) * p... precisely value < 2p << LOG2) -> canonical [0,p).
@@ -364,9 +429,14 @@ HADES_DEV void canon(Fr& out, const uint32_t (&r)[9]) {
     if constexpr (LOG2 >= 4) cond_sub_p_shl<4>(x, x8);
     if constexpr (LOG2 >= 3) cond_sub_p_shl<3>(x, x8);
     if constexpr (LOG2 >= 2) cond_sub_p_shl<2>(x, x8);
-    if constexpr (LOG2 >= 1) cond_sub_p_shl<1>(x, x8);
-    cond_sub_p_shl<0>(x, x8);
-    HADES_ASSERT(x8 == 0);
+    if constexpr (LOG2 >= 1) {
+        cond_sub_p_shl<1>(x, x8);
+        HADES_ASSERT(x8 == 0);  // < 2p < 2^256: the last subtraction runs on 8 limbs
+        cond_sub_p8(x);
+    } else {
+        cond_sub_p_shl<0>(x, x8);
+        HADES_ASSERT(x8 == 0);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) out.l[k] = x[k];
 }
@@ -379,8 +449,8 @@ HADES_DEV constexpr int canon_log2_for(int bound_p) {
 // out = a + b mod p, inputs canonical (scalar.rs:28 `*w += c`)
 HADES_DEV void fr_add(Fr& out, const Fr& a, const Fr& b) {
     uint32_t s[8];
-    uint32_t c = add8(s, a.l, b.l);  // a + b < 2p < 2^256: c == 0
-    cond_sub_p_shl<0>(s, c);
+    add8_nc(s, a.l, b.l);  // a + b < 2p < 2^256
+    cond_sub_p8(s);
 #pragma unroll
     for (int k = 0; k < 8; k++) out.l[k] = s[k];
 }

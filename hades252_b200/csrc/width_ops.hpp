@@ -1,6 +1,6 @@
 // Interface between the engine (C ABI, hades_engine.cu) and the per-width kernel translation units
-// (hades_w{3,5,9}.cu, hades_w{3,5,9}_dense.cu).  Each (width, algorithm) is its own TU because every
-// TU owns a separate 64 KB `__constant__` bank and the optimised tables alone need up to 62 KB.
+// (hades_w{3,5,9}_ccf.cu, hades_w{3,5,9}.cu, hades_w{3,5,9}_dense.cu).  Each (width, algorithm) is its own TU
+// because every TU owns a separate 64 KB `__constant__` bank and the derived tables alone need up to 57 KB.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -10,13 +10,13 @@ namespace hades {
 
 // Kernel variants (runtime-selectable so that bench/tests can A/B them; all bit-identical):
 //   algo 0 = dense schedule (reference round structure, one lazily reduced dot product per MDS row)
-//   algo 1 = optimised schedule (sparse partial rounds, host_tables.hpp)
-//   algo 2 = canonical-form schedule (time-invariant partial rounds in controller form, host_tables.hpp)
+//   algo 1 = sparse partial rounds (host_tables.hpp, derive_tables)
+//   algo 2 = gauged canonical-form schedule (host_tables.hpp, derive_tables_ccf) -- the default
 //   regs 0 = __launch_bounds__(128, 4) (<=128 registers), 1 = (128, 3) (<=168), 2 = (128, 2) (<=255),
 //   3 = (128, 5) (<=96); 4 / 5 = lockstep blocks of 256 / 512 threads with one barrier per round;
 //   6.. = lockstep 128-thread blocks (W=5: 6 -> 5 blocks/SM [default], 9 -> 4; W=3: 6 -> 7 [default], 7 -> 5;
 //   W=9: 6 -> 2, 7 -> 3 [default]); 7/8 at W=5 are 384/640-thread experiments
-//   (optimised perm kernel only; keeps the warps of a block on the same instruction-cache lines)
+//   (algo 1 and 2 only; the barrier keeps the warps of a block on the same instruction-cache lines)
 struct Variant {
     int algo;
     int regs;
