@@ -45,8 +45,8 @@ LIMB_PRODUCTS_PER_PERM = 268192   # 1972 Fr mul x 136 (8-limb CIOS), SURVEY.md 8
 EXECUTED_PRODUCTS = {2: 59 * 840 + 7 * 2920 + 3240 + 960, 1: 59 * 952 + 8 * 3240}
 EXECUTED_PRODUCTS_PER_PERM = EXECUTED_PRODUCTS[2]
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE default-kernel launch over 2^26 states, from the
-# `ncu --set full` capture summarised in profiles/r01_ncu_perm5_2p26_ccf_final.txt (10.836 + 10.702 GB)
-NCU_TRAFFIC_BYTES_2P26 = 21_537_614_000
+# `ncu --set full` capture summarised in profiles/r01_ncu_perm5_2p26_ccf_final.txt (10.839 + 10.702 GB)
+NCU_TRAFFIC_BYTES_2P26 = 21_540_254_000
 HBM_BYTES_PER_PERM = 2 * 32 * WIDTH
 SEED = 0x4861646573323532
 METRIC = "hades252_w5_perms_per_sec"
