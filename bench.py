@@ -481,6 +481,35 @@ def run_merkle(args):
             want = cpu_oracle.merkle_root(cpu_oracle.gen_elems(0, n, SEED))
             out["oracle_root_match"] = bool(np.array_equal(want, root_limbs))
             out["oracle_seconds"] = time.perf_counter() - t
+        if world == 1:
+            # resident tree (all levels kept) + batch of openings: the callers' side of the path
+            n_open = min(n, 1 << 20)
+            nodes = strat.merkle_tree_nodes(n)
+            levels = 0
+            m = n
+            while m > 1:
+                m = (m + 3) // 4
+                levels += 1
+            tree = torch.empty(nodes * 4, dtype=torch.int64, device="cuda")
+            idx = (torch.arange(n_open, dtype=torch.int64, device="cuda") * 2654435761) % n
+            branch = torch.empty(n_open * levels * 16, dtype=torch.int64, device="cuda")
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            strat.merkle_tree_device(leaves.data_ptr(), n, tree.data_ptr(), sp)
+            strat.merkle_open_device(leaves.data_ptr(), tree.data_ptr(), n, idx.data_ptr(), n_open, branch.data_ptr(), sp)
+            torch.cuda.synchronize()
+            ev[0].record(stream)
+            strat.merkle_tree_device(leaves.data_ptr(), n, tree.data_ptr(), sp)
+            ev[1].record(stream)
+            strat.merkle_open_device(leaves.data_ptr(), tree.data_ptr(), n, idx.data_ptr(), n_open, branch.data_ptr(), sp)
+            ev[2].record(stream)
+            torch.cuda.synchronize()
+            open_ms = ev[1].elapsed_time(ev[2])
+            tree_root = tree[-4:].cpu().numpy().view(np.uint64)
+            out["resident_tree"] = {"build_ms": ev[0].elapsed_time(ev[1]), "interior_nodes": nodes,
+                                    "root_equals_reduce_path": bool(np.array_equal(tree_root, root_limbs)),
+                                    "openings": {"n_open": n_open, "levels": levels, "ms": open_ms,
+                                                 "bytes_written": n_open * levels * 128,
+                                                 "GBps_written": n_open * levels * 128 / (open_ms * 1e-3) / 1e9}}
         emit(out)
     strat.close()
     if world > 1:

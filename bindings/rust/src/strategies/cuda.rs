@@ -85,6 +85,24 @@ impl CudaStrategy {
         Ok(())
     }
 
+    /// Root of the ragged 4-ary tree over any number of leaves: a node with `k < 4` children hashes
+    /// `perm([2^k - 1, c0, .., 0])[1]` (bitmask of the present children in word 0).
+    pub fn merkle_root_ragged(&mut self, leaves: &[BlsScalar]) -> Result<BlsScalar, CudaError> {
+        let mut root = BlsScalar::zero();
+        let rc = unsafe {
+            ffi::hades_merkle_root_ragged(
+                self.ctx,
+                leaves.as_ptr() as *const u64,
+                leaves.len(),
+                &mut root as *mut BlsScalar as *mut u64,
+            )
+        };
+        if rc != ffi::HADES_OK {
+            return Err(Self::error(self.ctx, rc));
+        }
+        Ok(root)
+    }
+
     /// Root of the 4-ary Merkle tree over `leaves` (`leaves.len()` must be a power of 4);
     /// node = `perm([15, c0, c1, c2, c3])[1]`.
     pub fn merkle_root(&mut self, leaves: &[BlsScalar]) -> Result<BlsScalar, CudaError> {

@@ -45,6 +45,32 @@ extern "C" {
         n_leaves: usize,
         root: *mut u64,
     ) -> c_int;
+    pub fn hades_merkle_tree_nodes(n_leaves: usize) -> usize;
+    pub fn hades_merkle_tree_dev(
+        ctx: *mut hades_ctx,
+        dev_index: c_int,
+        d_leaves: *const u64,
+        n_leaves: usize,
+        d_tree: *mut u64,
+        stream: *mut c_void,
+    ) -> c_int;
+    pub fn hades_merkle_open_dev(
+        ctx: *mut hades_ctx,
+        dev_index: c_int,
+        d_leaves: *const u64,
+        d_tree: *const u64,
+        n_leaves: usize,
+        d_index: *const u64,
+        n_open: usize,
+        d_branch: *mut u64,
+        stream: *mut c_void,
+    ) -> c_int;
+    pub fn hades_merkle_root_ragged(
+        ctx: *mut hades_ctx,
+        host_leaves: *const u64,
+        n_leaves: usize,
+        root: *mut u64,
+    ) -> c_int;
     pub fn hades_sponge_batch(
         ctx: *mut hades_ctx,
         elems: *const u64,

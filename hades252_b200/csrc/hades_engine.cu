@@ -133,7 +133,7 @@ int merkle_reduce(hades_ctx* ctx, const uint64_t* d_nodes, size_t n_nodes, int l
         size_t n_out = n / 4;
         uint64_t* out = (l == levels - 1) ? d_out : ((l & 1) ? bufB : bufA);
         ctx->launches++;
-        CUDA_TRY(ctx, ctx->ops()->launch_merkle_level(ctx->variant, in, out, n_out, stream));
+        CUDA_TRY(ctx, ctx->ops()->launch_merkle_level(ctx->variant, in, out, n_out, n, stream));
         in = out;
         n = n_out;
     }
@@ -328,6 +328,86 @@ int hades_merkle_reduce_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_nod
         return HADES_OK;
     }
     return merkle_reduce(ctx, d_nodes, n_nodes, levels, d_scratch, d_out, (cudaStream_t)stream);
+}
+
+size_t hades_merkle_tree_nodes(size_t n_leaves) {
+    size_t total = 0, m = n_leaves;
+    while (m > 1) {
+        m = (m + 3) / 4;
+        total += m;
+    }
+    return total;
+}
+
+int hades_merkle_tree_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leaves, size_t n_leaves, uint64_t* d_tree,
+                          void* stream) {
+    if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+    if (n_leaves == 0 || !d_leaves) return fail(ctx, HADES_ERR_INVALID_ARG, "a tree needs at least one leaf");
+    if (n_leaves == 1) return HADES_OK;  // the leaf is the root; no interior node
+    if (!d_tree) return fail(ctx, HADES_ERR_INVALID_ARG, "null tree pointer");
+    if (((uintptr_t)d_leaves | (uintptr_t)d_tree) & 15) return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    const uint64_t* in = d_leaves;
+    uint64_t* out = d_tree;
+    for (size_t m = n_leaves; m > 1;) {
+        const size_t n_out = (m + 3) / 4;
+        ctx->launches++;
+        CUDA_TRY(ctx, ctx->ops()->launch_merkle_level(ctx->variant, in, out, n_out, m, (cudaStream_t)stream));
+        in = out;
+        out += n_out * 4;
+        m = n_out;
+    }
+    return HADES_OK;
+}
+
+int hades_merkle_open_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leaves, const uint64_t* d_tree, size_t n_leaves,
+                          const uint64_t* d_index, size_t n_open, uint64_t* d_branch, void* stream) {
+    if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    if (n_leaves == 0 || !d_leaves) return fail(ctx, HADES_ERR_INVALID_ARG, "a tree needs at least one leaf");
+    int levels = 0;
+    for (size_t m = n_leaves; m > 1; m = (m + 3) / 4) levels++;
+    if (n_open == 0 || levels == 0) return HADES_OK;  // nothing to write (a single leaf has an empty path)
+    if (!d_tree || !d_index || !d_branch) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    if (((uintptr_t)d_leaves | (uintptr_t)d_tree | (uintptr_t)d_branch) & 15)
+        return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    const size_t chunks = n_open * (size_t)levels * 8;
+    const unsigned blocks = (unsigned)std::min<size_t>((chunks + 255) / 256, 148 * 16);
+    merkle_open_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(d_leaves),
+                                                                 reinterpret_cast<const uint4*>(d_tree), n_leaves, d_index, n_open,
+                                                                 levels, reinterpret_cast<uint4*>(d_branch));
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HADES_OK;
+}
+
+int hades_merkle_root_ragged(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]) {
+    if (!ctx || !host_leaves || !root) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+    if (n_leaves == 0) return fail(ctx, HADES_ERR_INVALID_ARG, "a tree needs at least one leaf");
+    if (n_leaves == 1) {
+        memcpy(root, host_leaves, 32);
+        return HADES_OK;
+    }
+    DeviceState& d = ctx->devs[0];
+    uint64_t *d_leaves = nullptr, *d_tree = nullptr;
+    const size_t nodes = hades_merkle_tree_nodes(n_leaves);
+    auto step = [&]() -> int {
+        CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+        CUDA_TRY(ctx, cudaMalloc(&d_leaves, n_leaves * 32));
+        CUDA_TRY(ctx, cudaMalloc(&d_tree, nodes * 32));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_leaves, host_leaves, n_leaves * 32, cudaMemcpyHostToDevice, d.streams[0]));
+        int r = hades_merkle_tree_dev(ctx, 0, d_leaves, n_leaves, d_tree, d.streams[0]);
+        if (r) return r;
+        CUDA_TRY(ctx, cudaMemcpyAsync(root, d_tree + (nodes - 1) * 4, 32, cudaMemcpyDeviceToHost, d.streams[0]));
+        CUDA_TRY(ctx, cudaStreamSynchronize(d.streams[0]));
+        return HADES_OK;
+    };
+    int rc = step();
+    cudaFree(d_leaves);
+    cudaFree(d_tree);
+    return rc;
 }
 
 int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]) {

@@ -46,6 +46,32 @@ __global__ void digest_kernel(const uint64_t* __restrict__ limbs, uint64_t first
     }
 }
 
+// ---- Merkle openings: gather the authentication paths of n_open leaves out of a resident tree -----------
+// tree = interior levels of the ragged 4-ary tree, level 1 first, root last (hades_merkle_tree_dev).
+// branch[o][l][c] = child c of the level-(l+1) ancestor of leaf index[o] (the path node included), zero when the
+// child does not exist.  One thread per 16-byte chunk: HBM-bound gather, coalesced on the output side.
+__global__ void merkle_open_kernel(const uint4* __restrict__ leaves, const uint4* __restrict__ tree, size_t n_leaves,
+                                   const uint64_t* __restrict__ index, size_t n_open, int levels, uint4* __restrict__ branch) {
+    const size_t total = n_open * (size_t)levels * 8;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int half = (int)(t & 1), c = (int)((t >> 1) & 3);
+        const size_t ol = t >> 3;
+        const int l = (int)(ol % levels);
+        const size_t o = ol / levels;
+        // size of level l and offset of level l inside `tree` (level 0 = the leaves)
+        size_t m = n_leaves, off = 0;
+        for (int k = 0; k < l; k++) {
+            m = (m + 3) / 4;
+            if (k + 1 < l) off += m;
+        }
+        // after the loop: m = size of level l; off = sum of sizes of levels 1 .. l-1
+        const size_t g = 4 * ((index[o] >> (2 * l)) / 4) + c;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (g < m) v = (l == 0 ? leaves : tree + off * 2)[g * 2 + half];
+        branch[t] = v;
+    }
+}
+
 // sponge length bucketing: key = permutations needed by message m = floor(len / 4) + 1, value = m
 __global__ void sponge_keys_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ keys,
                                    uint32_t* __restrict__ idx, size_t n_msgs) {

@@ -170,22 +170,41 @@ __device__ __forceinline__ void fr_set_fifteen(Fr& x) {  // 15 * R mod p (Merkle
 #pragma unroll
     for (int k = 0; k < 8; k++) x.l[k] = v[k];
 }
+// Montgomery forms of the Merkle bitmasks 2^k - 1 for k = 1..4 present children (ragged trees; checked in tests)
+__device__ const uint32_t kMaskMont[4][8] = {
+    {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u},   // 1
+    {0xfffffffau, 0x00000005u, 0x0009d806u, 0x098e27eeu, 0xc634efe0u, 0xcca4efcfu, 0x064f104eu, 0x486e140du},   // 3
+    {0xfffffff1u, 0x0000000eu, 0x00189c0fu, 0x17e363d3u, 0x6f8457b0u, 0xff9c5787u, 0x8fc5a8c4u, 0x35133220u},   // 7
+    {0xffffffdfu, 0x00000020u, 0x00362421u, 0x348ddb9du, 0xc2232750u, 0x658b26f6u, 0xa2b2d9b1u, 0x0e5d6e47u}};  // 15
+// word 0 of a Merkle node with `present` (1..4) children; only the last node of a level can have fewer than 4
+__device__ __forceinline__ void fr_set_mask(Fr& x, int present) {
+    fr_set_fifteen(x);
+    if (present < 4) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) x.l[k] = kMaskMont[present > 0 ? present - 1 : 0][k];
+    }
+}
 __device__ __forceinline__ void fr_set_zero(Fr& x) {
 #pragma unroll
     for (int k = 0; k < 8; k++) x.l[k] = 0;
 }
 
-// ---- merkle level: out[i] = perm([15, in[4i], in[4i+1], in[4i+2], in[4i+3]])[1] ---------------------
+// ---- merkle level: out[i] = perm([2^k - 1, in[4i], ..., in[4i+k-1], 0 ...])[1], k = children present (4 except
+// possibly for the last node of a ragged level: n_in = number of nodes of the input level, n_out = ceil(n_in / 4))
 template <int ALGO, int MINB>
 __global__ void __launch_bounds__(kPermThreads, MINB)
-merkle_level_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out) {
+merkle_level_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out, size_t n_in) {
     size_t i = (size_t)blockIdx.x * kPermThreads + threadIdx.x;
     if (i >= n_out) return;
+    const int present = n_in - 4 * i < 4 ? (int)(n_in - 4 * i) : 4;
     Fr s[5];
-    fr_set_fifteen(s[0]);
+    fr_set_mask(s[0], present);
     const uint4* p = in + i * 8;  // 4 children = 128 contiguous bytes
 #pragma unroll
-    for (int j = 0; j < 4; j++) fr_load(s[1 + j], p + 2 * j);
+    for (int j = 0; j < 4; j++) {
+        if (j < present) fr_load(s[1 + j], p + 2 * j);
+        else fr_set_zero(s[1 + j]);
+    }
     permute<ALGO>(s);
     fr_store(out + i * 2, s[1]);
 }
@@ -195,7 +214,7 @@ merkle_level_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_
 // warp's 32 x 128 B of children are moved with coalesced 128-bit loads through padded shared memory.
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out) {
+merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out, size_t n_in) {
     constexpr int kPitch = 9;  // 8 chunks of children + 1 pad: conflict-free 128-bit reads
     __shared__ uint4 stage[BLOCK * kPitch];
     const int lane = threadIdx.x & 31;
@@ -207,15 +226,19 @@ merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ o
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int c = lane + 32 * k, st = c >> 3, off = c & 7;
-        if (st < n_in_warp) tile[st * kPitch + off] = gbase[c];
+        // chunk c = half of child (off >> 1) of node warp_first + st; a ragged level ends inside a node
+        if (st < n_in_warp && 4 * (warp_first + st) + (off >> 1) < n_in) tile[st * kPitch + off] = gbase[c];
     }
     __syncwarp();
     Fr s[5];
-    fr_set_fifteen(s[0]);
-    const uint4* mine = tile + (live ? lane : 0) * kPitch;
+    const int my = live ? lane : 0;  // dead lanes recompute the warp's first node and store nothing
+    const size_t first_child = 4 * (warp_first + my);
+    const int present = n_in_warp == 0 ? 0 : (n_in - first_child < 4 ? (int)(n_in - first_child) : 4);
+    fr_set_mask(s[0], present);
+    const uint4* mine = tile + my * kPitch;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        if (n_in_warp > 0) fr_load(s[1 + j], mine + 2 * j);
+        if (j < present) fr_load(s[1 + j], mine + 2 * j);
         else fr_set_zero(s[1 + j]);
     }
     permute_fast<BlockSync>(s);
@@ -366,12 +389,13 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
 }
 
 #if HADES_W == 5
-cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s) {
+cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, size_t n_in, cudaStream_t s) {
     if (n_out == 0) return cudaSuccess;
+    if (n_in > 4 * n_out || n_in + 3 < 4 * n_out) return cudaErrorInvalidValue;  // n_out == ceil(n_in / 4)
 #if HADES_ALGO >= 1
     if (v.regs >= 4) {  // lockstep launch shapes share one Merkle build
         merkle_level_lockstep_kernel<128, 5><<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(
-            reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out);
+            reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out, n_in);
         return cudaGetLastError();
     }
 #endif
@@ -379,7 +403,7 @@ cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out
     size_t blocks = (n_out + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     HADES_DISPATCH(merkle_level_kernel, v,
-                   <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out));
+                   <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out, n_in));
     return cudaGetLastError();
 }
 cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,

@@ -30,7 +30,8 @@ struct WidthOps {
     cudaError_t (*upload)(const uint64_t* table);  // to the CURRENT device
     cudaError_t (*launch_perm)(Variant v, uint64_t* d_states, size_t n, cudaStream_t s);
     // width 5 only (nullptr otherwise)
-    cudaError_t (*launch_merkle_level)(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, cudaStream_t s);
+    // n_out == ceil(n_in / 4); the last node of a ragged level hashes its present children under the matching bitmask
+    cudaError_t (*launch_merkle_level)(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, size_t n_in, cudaStream_t s);
     cudaError_t (*launch_sponge)(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
                                  uint64_t* d_out, size_t n_threads, cudaStream_t s);
     cudaError_t (*func_attributes)(const char* kernel, Variant v, cudaFuncAttributes* out);

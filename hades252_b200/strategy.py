@@ -134,6 +134,29 @@ class CudaStrategy(Strategy):
         self._check(self._lib.hades_merkle_reduce_dev(self._ctx, dev_index, nodes_ptr, n_nodes, levels, scratch_ptr,
                                                       out_ptr, stream))
 
+    # ragged tree + openings (include/hades_cuda.h: any number of leaves, partial nodes under their bitmask)
+    def merkle_tree_nodes(self, n_leaves: int) -> int:
+        return int(self._lib.hades_merkle_tree_nodes(n_leaves))
+
+    def merkle_root_ragged(self, leaves: np.ndarray) -> np.ndarray:
+        _as_u64(leaves, "leaves")
+        if leaves.ndim != 2 or leaves.shape[1] != 4:
+            raise ValueError("leaves must have shape [n, 4]")
+        root = np.empty(4, dtype=np.uint64)
+        self._check(self._lib.hades_merkle_root_ragged(self._ctx, leaves.ctypes.data, leaves.shape[0],
+                                                       root.ctypes.data_as(_native.u64p)))
+        return root
+
+    def merkle_tree_device(self, leaves_ptr: int, n_leaves: int, tree_ptr: int, stream: int = 0, dev_index: int = 0) -> None:
+        """all interior levels (level 1 first, root last) of the ragged tree into device memory at tree_ptr"""
+        self._check(self._lib.hades_merkle_tree_dev(self._ctx, dev_index, leaves_ptr, n_leaves, tree_ptr, stream))
+
+    def merkle_open_device(self, leaves_ptr: int, tree_ptr: int, n_leaves: int, index_ptr: int, n_open: int,
+                           branch_ptr: int, stream: int = 0, dev_index: int = 0) -> None:
+        """authentication paths [n_open, levels, 4, 4] u64 of the leaves listed at index_ptr (u64 positions)"""
+        self._check(self._lib.hades_merkle_open_dev(self._ctx, dev_index, leaves_ptr, tree_ptr, n_leaves, index_ptr, n_open,
+                                                    branch_ptr, stream))
+
     def sponge_batch(self, elems: np.ndarray, offsets: np.ndarray) -> np.ndarray:
         """Sponge digests of n messages in CSR form; elems uint64 [total, 4], offsets uint64 [n+1]."""
         _as_u64(offsets, "offsets")

@@ -105,6 +105,28 @@ int hades_merkle_reduce_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_nod
                             int levels, uint64_t* d_scratch, uint64_t* d_out, void* stream);
 
 /*
+ * Ragged 4-ary Merkle tree over ANY number of leaves, kept resident for openings (the callers of `perm`
+ * in dusk-poseidon hash partially filled nodes under a bitmask of the present children and hand out
+ * authentication paths; SURVEY.md 8(f)4 -- build-defined like hades_merkle_root): a level of m nodes has
+ * ceil(m/4) parents; a parent with k present children = perm([2^k - 1, c_0 .. c_{k-1}, 0 ...])[1].  For
+ * n_leaves = 4^d the root equals hades_merkle_root's.
+ *   hades_merkle_tree_nodes(n)  number of interior nodes (all levels above the leaves); 0 for n <= 1
+ *   hades_merkle_tree_dev       writes the interior levels to d_tree (level 1 first, root last:
+ *                               hades_merkle_tree_nodes(n) elements of 32 B); asynchronous on `stream`
+ *   hades_merkle_open_dev       authentication paths of n_open leaves (d_index: their positions) from a
+ *                               resident tree: d_branch[o][l][c] (32 B each, l < number of levels, c < 4) =
+ *                               child c of the level-(l+1) ancestor of leaf d_index[o], the path node
+ *                               included, zero where the child does not exist; asynchronous on `stream`
+ *   hades_merkle_root_ragged    HOST leaves -> root, on the context's first device
+ */
+size_t hades_merkle_tree_nodes(size_t n_leaves);
+int hades_merkle_tree_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leaves, size_t n_leaves, uint64_t* d_tree,
+                          void* stream);
+int hades_merkle_open_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leaves, const uint64_t* d_tree, size_t n_leaves,
+                          const uint64_t* d_index, size_t n_open, uint64_t* d_branch, void* stream);
+int hades_merkle_root_ragged(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]);
+
+/*
  * Sponge hash (rate 4, capacity 1) of n_msgs variable-length messages given in CSR form:
  * message m = elems[offsets[m] .. offsets[m+1]) (field elements, 32 B each).  State [0;5]; the
  * message is padded with a single 1 then zeros to a multiple of 4 (always at least the 1); each

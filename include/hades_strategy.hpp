@@ -75,6 +75,12 @@ public:
         check(hades_merkle_root(ctx_, leaves.empty() ? nullptr : &leaves[0].limbs[0], leaves.size(), root.limbs));
         return root;
     }
+    // ragged tree: any number of leaves, partial nodes hashed under the bitmask of their present children
+    BlsScalar merkle_root_ragged(const std::vector<BlsScalar>& leaves) {
+        BlsScalar root{};
+        check(hades_merkle_root_ragged(ctx_, leaves.empty() ? nullptr : &leaves[0].limbs[0], leaves.size(), root.limbs));
+        return root;
+    }
     std::vector<BlsScalar> sponge_batch(const std::vector<BlsScalar>& elems, const std::vector<std::uint64_t>& offsets) {
         if (offsets.empty()) throw std::invalid_argument("offsets needs n + 1 entries");
         std::vector<BlsScalar> out(offsets.size() - 1);

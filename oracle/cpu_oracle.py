@@ -37,6 +37,10 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_perm.restype = ctypes.c_int
         _lib.oracle_merkle_root.argtypes = [_u64p, ctypes.c_size_t, _u64p, _u64p, _u64p, ctypes.c_int]
         _lib.oracle_merkle_root.restype = ctypes.c_int
+        _lib.oracle_merkle_tree_nodes.argtypes = [ctypes.c_size_t]
+        _lib.oracle_merkle_tree_nodes.restype = ctypes.c_size_t
+        _lib.oracle_merkle_tree.argtypes = [_u64p, ctypes.c_size_t, _u64p, _u64p, _u64p, ctypes.c_int]
+        _lib.oracle_merkle_tree.restype = ctypes.c_int
         _lib.oracle_sponge_batch.argtypes = [_u64p, _u64p, ctypes.c_size_t, _u64p, _u64p, _u64p, ctypes.c_int]
         _lib.oracle_sponge_batch.restype = ctypes.c_int
         _lib.oracle_load_table.argtypes = [_u8p, ctypes.c_size_t, _u64p]
@@ -115,6 +119,40 @@ def sponge_batch(elems: np.ndarray, offsets: np.ndarray, nthreads: int | None = 
     lib().oracle_sponge_batch(_p(elems), _p(offsets), n, _p(ark), _p(mds), _p(out),
                               nthreads or host_threads())
     return out
+
+
+def merkle_level_sizes(n_leaves: int) -> list:
+    """sizes of the interior levels of the ragged tree, level 1 first, root last"""
+    sizes, m = [], n_leaves
+    while m > 1:
+        m = (m + 3) // 4
+        sizes.append(m)
+    return sizes
+
+
+def merkle_tree(leaves: np.ndarray, nthreads: int | None = None) -> np.ndarray:
+    """Ragged 4-ary tree over any number of leaves (hades_ref.merkle_levels): all interior levels,
+    level 1 first, root last, uint64 [nodes, 4]."""
+    leaves = np.ascontiguousarray(leaves, dtype=np.uint64).reshape(-1, 4)
+    ark, mds = tables(5)
+    tree = np.empty((lib().oracle_merkle_tree_nodes(leaves.shape[0]), 4), dtype=np.uint64)
+    if lib().oracle_merkle_tree(_p(leaves), leaves.shape[0], _p(ark), _p(mds), _p(tree), nthreads or host_threads()):
+        raise ValueError("oracle_merkle_tree: need at least one leaf")
+    return tree
+
+
+def merkle_opening(leaves: np.ndarray, tree: np.ndarray, index: int) -> np.ndarray:
+    """branch [levels, 4, 4] of leaf `index` taken from a tree built by merkle_tree (absent children zero)."""
+    leaves = np.ascontiguousarray(leaves, dtype=np.uint64).reshape(-1, 4)
+    sizes = merkle_level_sizes(leaves.shape[0])
+    branch = np.zeros((len(sizes), 4, 4), dtype=np.uint64)
+    cur, i, off = leaves, index, 0
+    for l, m in enumerate(sizes):
+        g = 4 * (i // 4)
+        k = min(4, cur.shape[0] - g)
+        branch[l, :k] = cur[g:g + k]
+        cur, off, i = tree[off:off + m], off + m, i // 4
+    return branch
 
 
 def gen_elems(first_elem: int, n_elems: int, seed: int = hades_ref.SEED) -> np.ndarray:

@@ -228,6 +228,42 @@ int oracle_merkle_root(const uint64_t *leaves, size_t n_leaves, const uint64_t *
     return 0;
 }
 
+/* Ragged tree (any n_leaves >= 1), all interior levels written to `tree` (level 1 first, root last;
+ * oracle_merkle_tree_nodes(n) nodes): a parent with k present children = perm([2^k - 1, c.., 0..])[1].
+ * Restates oracle/hades_ref.py merkle_levels (build-defined convention). */
+typedef struct { const fr_t *in; fr_t *out; size_t n_in; const fr_t *ark, *mds; fr_t mask[5]; } rtree_ctx;
+static void rtree_range(void *p, size_t lo, size_t hi) {
+    rtree_ctx *c = p;
+    for (size_t i = lo; i < hi; i++) {
+        size_t k = c->n_in - 4 * i; if (k > 4) k = 4;
+        fr_t s[5]; memset(s, 0, sizeof s);
+        s[0] = c->mask[k];
+        memcpy(&s[1], &c->in[4 * i], k * sizeof(fr_t));
+        perm_one(s, 5, c->ark, c->mds);
+        c->out[i] = s[1];
+    }
+}
+size_t oracle_merkle_tree_nodes(size_t n_leaves) {
+    size_t total = 0, m = n_leaves;
+    while (m > 1) { m = (m + 3) / 4; total += m; }
+    return total;
+}
+int oracle_merkle_tree(const uint64_t *leaves, size_t n_leaves, const uint64_t *ark, const uint64_t *mds,
+                       uint64_t *tree, int nthreads) {
+    if (n_leaves == 0) return 1;
+    rtree_ctx c; c.ark = (const fr_t *)ark; c.mds = (const fr_t *)mds;
+    for (uint64_t k = 1; k <= 4; k++) { uint64_t raw[4] = {(1ULL << k) - 1, 0, 0, 0}; oracle_from_raw(raw, c.mask[k].l); }
+    const fr_t *in = (const fr_t *)leaves; fr_t *out = (fr_t *)tree;
+    size_t m = n_leaves;
+    while (m > 1) {
+        size_t n_out = (m + 3) / 4;
+        c.in = in; c.out = out; c.n_in = m;
+        parallel_for(n_out, nthreads, rtree_range, &c);
+        in = out; out += n_out; m = n_out;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------- sponge */
 typedef struct { const fr_t *elems; const uint64_t *off; fr_t *out; const fr_t *ark, *mds; fr_t one; } sponge_ctx;
 static void sponge_range(void *p, size_t lo, size_t hi) {

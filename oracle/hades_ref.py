@@ -206,6 +206,56 @@ def merkle_root(leaves: Sequence[int]) -> int:
     return level[0]
 
 
+# Ragged 4-ary tree (any number of leaves) and openings -- the "partial bitmask" convention of the Merkle
+# callers: a level of m nodes has ceil(m/4) parents; a parent with k present
+# children hashes perm([2^k - 1, c_0 .. c_{k-1}, 0 ...])[1] (word 0 = bitmask of the present children,
+# absent children are zero).  For 4^d leaves every mask is 0b1111 and the root equals merkle_root().
+def merkle_node_partial(children: Sequence[int]) -> int:
+    k = len(children)
+    assert 1 <= k <= MERKLE_ARITY
+    return perm([(1 << k) - 1, *children, *([0] * (MERKLE_ARITY - k))])[1]
+
+
+def merkle_levels(leaves: Sequence[int]) -> List[List[int]]:
+    """levels[0] = leaves, ..., levels[-1] = [root]."""
+    if len(leaves) < 1:
+        raise ValueError("at least one leaf")
+    levels = [[x % P for x in leaves]]
+    while len(levels[-1]) > 1:
+        cur = levels[-1]
+        levels.append([merkle_node_partial(cur[i:i + 4]) for i in range(0, len(cur), 4)])
+    return levels
+
+
+def merkle_root_ragged(leaves: Sequence[int]) -> int:
+    return merkle_levels(leaves)[-1][0]
+
+
+def merkle_opening(leaves: Sequence[int], index: int) -> List[List[int]]:
+    """Authentication path of leaf `index`: per level the 4 children of the path's parent (the path node
+    included, absent children as 0)."""
+    levels = merkle_levels(leaves)
+    branch, i = [], index
+    for cur in levels[:-1]:
+        g = 4 * (i // 4)
+        branch.append([cur[g + c] if g + c < len(cur) else 0 for c in range(4)])
+        i //= 4
+    return branch
+
+
+def merkle_verify(leaf: int, index: int, n_leaves: int, branch: Sequence[Sequence[int]], root: int) -> bool:
+    node, i, m = leaf % P, index, n_leaves
+    for group in branch:
+        if group[i % 4] != node:
+            return False
+        k = min(4, m - 4 * (i // 4))
+        if any(group[c] != 0 for c in range(k, 4)):
+            return False
+        node = merkle_node_partial(list(group[:k]))
+        i, m = i // 4, (m + 3) // 4
+    return m == 1 and node == root
+
+
 def sponge(message: Iterable[int]) -> int:
     """rate 4 / capacity 1: state [0;5]; pad with one 1 then zeros to a multiple of 4;
     per block add the 4 elements into words 1..4 and perm; output word 1."""

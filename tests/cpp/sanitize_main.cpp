@@ -22,7 +22,7 @@ int main() {
         std::printf("init: %s\n", hades_last_error(nullptr));
         return 77;
     }
-    for (int algo = 0; algo < 2; algo++)
+    for (int algo = 0; algo < 3; algo++)
         for (int regs : {0, 6}) {
             if (algo == 0 && regs == 6) continue;
             CHECK(hades_set_variant(ctx, algo, regs));
@@ -35,6 +35,7 @@ int main() {
             fill(leaves);
             uint64_t root[4];
             CHECK(hades_merkle_root(ctx, leaves.data(), 256, root));
+            for (size_t nl : {2, 5, 130, 255}) CHECK(hades_merkle_root_ragged(ctx, leaves.data(), nl, root));
             std::vector<uint64_t> offsets(201);
             offsets[0] = 0;
             for (int m = 0; m < 200; m++) offsets[m + 1] = offsets[m] + (next() % 11);

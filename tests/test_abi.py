@@ -107,3 +107,20 @@ def test_device_small_constants():
         words = re.findall(r"0x([0-9a-f]{8})u", body)[:8]
         got = sum(int(w, 16) << (32 * i) for i, w in enumerate(words))
         assert got == val * H.R % H.P, name
+
+
+def test_device_merkle_bitmask_constants():
+    """Montgomery forms of the bitmasks 1, 3, 7, 15 of partially filled Merkle nodes (kMaskMont)."""
+    from oracle import hades_ref as H
+    src = open(os.path.join(ROOT, "hades252_b200", "csrc", "width_impl.cuh")).read()
+    body = src[src.index("kMaskMont[4][8]"):]
+    words = re.findall(r"0x([0-9a-f]{8})u", body)[:32]
+    for k in range(4):
+        got = sum(int(w, 16) << (32 * i) for i, w in enumerate(words[8 * k:8 * k + 8]))
+        assert got == ((1 << (k + 1)) - 1) * H.R % H.P
+
+
+def test_merkle_tree_nodes_host_helper(lib):
+    from oracle import cpu_oracle as C
+    for n in (0, 1, 2, 4, 5, 16, 17, 1000, 4 ** 12, 4 ** 12 + 1):
+        assert lib.hades_merkle_tree_nodes(n) == sum(C.merkle_level_sizes(n))

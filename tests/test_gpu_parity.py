@@ -462,3 +462,57 @@ def test_custom_constants_all_schedules(w):
     res = subprocess.run([sys.executable, "-c", _CUSTOM_CONSTANTS_SCRIPT, str(w)], cwd=root, capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and "custom constants OK" in res.stdout, res.stdout + res.stderr
+
+
+# ---- ragged Merkle tree + openings (partially filled nodes under a bitmask, paths) -------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 17, 63, 64, 65, 1000, 4097, 4 ** 8 + 3])
+def test_merkle_root_ragged(cuda_strategy, oracle, n):
+    leaves = oracle.gen_elems(31 + n, n)
+    got = cuda_strategy.merkle_root_ragged(leaves)
+    want = oracle.merkle_tree(leaves)[-1] if n > 1 else leaves[0]
+    assert np.array_equal(got, want)
+    if n in (4, 64):
+        assert np.array_equal(got, cuda_strategy.merkle_root(leaves))
+
+
+@pytest.mark.parametrize("algo,regs", [(2, 6), (2, 0), (1, 6), (0, 0)])
+def test_merkle_tree_and_openings_device(oracle, H, algo, regs):
+    import torch
+    from hades252_b200 import CudaStrategy
+    n = 3 * 4 ** 6 + 1234  # 13522 leaves: ragged on several levels
+    leaves = oracle.gen_elems(777, n)
+    want_tree = oracle.merkle_tree(leaves)
+    with CudaStrategy([0]) as s:
+        s.set_variant(algo, regs)
+        assert s.merkle_tree_nodes(n) == want_tree.shape[0]
+        d_leaves = torch.from_numpy(leaves.view(np.int64)).cuda()
+        d_tree = torch.empty((want_tree.shape[0], 4), dtype=torch.int64, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        s.merkle_tree_device(d_leaves.data_ptr(), n, d_tree.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_tree.cpu().numpy().view(np.uint64), want_tree)
+        # openings of a few hundred leaves, including both ends and the ragged tail
+        idx = np.unique(np.concatenate([[0, 1, 3, 4, n - 1, n - 2, n - 5], np.arange(0, n, 53)])).astype(np.uint64)
+        levels = len(oracle.merkle_level_sizes(n))
+        d_idx = torch.from_numpy(idx.view(np.int64)).cuda()
+        d_branch = torch.empty((idx.shape[0], levels, 4, 4), dtype=torch.int64, device="cuda")
+        s.merkle_open_device(d_leaves.data_ptr(), d_tree.data_ptr(), n, d_idx.data_ptr(), idx.shape[0], d_branch.data_ptr(), stream)
+        torch.cuda.synchronize()
+        branch = d_branch.cpu().numpy().view(np.uint64)
+        for o, i in enumerate(idx):
+            assert np.array_equal(branch[o], oracle.merkle_opening(leaves, want_tree, int(i)))
+        # one path re-verified from scratch with the big-int reference (root recomputed from the branch)
+        root = H.from_mont_limbs([int(x) for x in want_tree[-1]])
+        o = len(idx) // 2
+        path = [[H.from_mont_limbs([int(x) for x in node]) for node in group] for group in branch[o]]
+        leaf = H.from_mont_limbs([int(x) for x in leaves[int(idx[o])]])
+        assert H.merkle_verify(leaf, int(idx[o]), n, path, root)
+
+
+def test_merkle_tree_single_leaf_and_errors(cuda_strategy, oracle):
+    from hades252_b200 import HadesError
+    leaf = oracle.gen_elems(5, 1)
+    assert np.array_equal(cuda_strategy.merkle_root_ragged(leaf), leaf[0])
+    assert cuda_strategy.merkle_tree_nodes(1) == 0
+    with pytest.raises(HadesError):
+        cuda_strategy.merkle_root_ragged(np.empty((0, 4), dtype=np.uint64))

@@ -175,3 +175,40 @@ def test_wrong_length_rejected():
         H.perm([1, 2, 3, 4], width=5)
     with pytest.raises(ValueError):
         H.perm([1] * 15)  # 67*15 > 960
+
+
+# ---- ragged Merkle tree and openings (build-defined convention) ---------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 16, 17, 21, 64, 67])
+def test_ragged_merkle_python_vs_c(n):
+    from oracle import cpu_oracle as C
+    leaves = C.gen_elems(900 + n, n)
+    vals = [H.from_mont_limbs([int(x) for x in leaf]) for leaf in leaves]
+    levels = H.merkle_levels(vals)
+    tree = C.merkle_tree(leaves)
+    assert tree.shape[0] == sum(len(lv) for lv in levels[1:]) == sum(C.merkle_level_sizes(n))
+    flat = [v for lv in levels[1:] for v in lv]
+    for node, want in zip(tree, flat):
+        assert [int(x) for x in node] == H.to_mont_limbs(want)
+    if n in (1, 4, 16, 64):  # all masks 0b1111: same root as the power-of-4 tree
+        assert H.merkle_root_ragged(vals) == H.merkle_root(vals)
+        if n > 1:
+            assert np.array_equal(tree[-1], C.merkle_root(leaves))
+
+
+def test_merkle_openings_verify_and_reject_tampering():
+    from oracle import cpu_oracle as C
+    n = 23
+    leaves = C.gen_elems(4321, n)
+    vals = [H.from_mont_limbs([int(x) for x in leaf]) for leaf in leaves]
+    root = H.merkle_root_ragged(vals)
+    tree = C.merkle_tree(leaves)
+    for i in (0, 3, 4, 19, 20, 22):
+        branch = H.merkle_opening(vals, i)
+        assert H.merkle_verify(vals[i], i, n, branch, root)
+        got = C.merkle_opening(leaves, tree, i)
+        assert [[H.from_mont_limbs([int(x) for x in node]) for node in group] for group in got] == branch
+        assert not H.merkle_verify((vals[i] + 1) % H.P, i, n, branch, root)
+        bad = [list(g) for g in branch]
+        bad[-1][0] = (bad[-1][0] + 1) % H.P
+        assert not H.merkle_verify(vals[i], i, n, bad, root)
+    assert not H.merkle_verify(vals[0], 1, n, H.merkle_opening(vals, 0), root)
