@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhades_b200.so")
+# HADES_B200_LIB: an alternative build of the same library (kernel A/B experiments under tools/)
+LIB_PATH = os.environ.get("HADES_B200_LIB") or os.path.join(_HERE, "lib", "libhades_b200.so")
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 ctx_p = ctypes.c_void_p
@@ -42,6 +43,7 @@ SIGNATURES = {
     "hades_kernel_info": (ctypes.c_int, [ctx_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int),
                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "hades_set_variant": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_int]),
+    "hades_set_coop_threshold": (ctypes.c_int, [ctx_p, ctypes.c_size_t]),
     "hades_launch_count": (ctypes.c_uint64, [ctx_p]),
 }
 

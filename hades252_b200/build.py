@@ -11,8 +11,20 @@ LIB = os.path.join(HERE, "lib", "libhades_b200.so")
 SOURCES = ["hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu",
            "hades_w3_dense.cu", "hades_w5_dense.cu", "hades_w9_dense.cu",
            "hades_w3_ccf.cu", "hades_w5_ccf.cu", "hades_w9_ccf.cu", "hades_generic.cu"]
-HEADERS = ["fr.cuh", "hades.cuh", "width_impl.cuh", "width_ops.hpp", "util_kernels.cuh", "host_tables.hpp",
+HEADERS = ["fr.cuh", "hades.cuh", "coop.cuh", "width_impl.cuh", "width_ops.hpp", "util_kernels.cuh", "host_tables.hpp",
            os.path.join("..", "..", "include", "hades_cuda.h")]
+_KERNEL_HDRS = ["fr.cuh", "hades.cuh", "width_impl.cuh", "width_ops.hpp"]
+
+
+def _deps(src: str):
+    """headers a translation unit includes (an object is rebuilt only when one of them is newer)"""
+    if src == "hades_engine.cu":
+        return ["fr.cuh", "host_tables.hpp", "util_kernels.cuh", "width_ops.hpp", os.path.join("..", "..", "include", "hades_cuda.h")]
+    if src == "hades_generic.cu":
+        return ["fr.cuh", "hades.cuh", "width_ops.hpp"]
+    if src == "hades_w5_ccf.cu":
+        return _KERNEL_HDRS + ["coop.cuh"]
+    return _KERNEL_HDRS
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -26,8 +38,6 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """One nvcc -c per translation unit (in parallel), then one link into the shared library."""
-    if not force and not _stale():
-        return LIB
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objdir = os.path.join(HERE, "lib", "obj")
@@ -38,7 +48,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", "-o", obj, os.path.join(CSRC, src)]
+        stamp = obj + ".cmd"   # the command line and ptxas report of the object on disk
+        fresh = (not force and os.path.exists(obj) and os.path.exists(stamp)
+                 and open(stamp).readline().rstrip("\n") == " ".join(cmd)
+                 and all(os.path.getmtime(os.path.join(CSRC, f)) <= os.path.getmtime(obj) for f in [src] + _deps(src)))
+        if fresh:
+            res = subprocess.CompletedProcess(cmd, 0, stdout=open(stamp).read().split("\n", 1)[1])
+            res.fresh = True
+            return src, obj, cmd, res
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode == 0:
+            with open(stamp, "w") as f:
+                f.write(" ".join(cmd) + "\n" + res.stdout)
         return src, obj, cmd, res
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
@@ -52,6 +73,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stdout)
         if res.returncode:
             raise RuntimeError(f"nvcc failed on {src} ({res.returncode}); see {log}")
+    if (os.path.exists(LIB) and all(getattr(r[3], "fresh", False) for r in results)
+            and all(os.path.getmtime(r[1]) <= os.path.getmtime(LIB) for r in results)):
+        return LIB
     link = [nvcc, "-shared", "-cudart", "static", "-o", LIB, *[r[1] for r in results]]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(log, "a") as f:

@@ -1,0 +1,304 @@
+// Cooperative (low-latency) Hades252 permutation: ONE width-5 state per group of 8 lanes.
+//
+// Why: the one-thread-per-state kernels are throughput kernels.  A lone warp needs ~270 us for its 74 200
+// dependent-ish limb products, so every batch below ~2^14 states -- a lone `Strategy::perm`
+// (src/strategies.rs:140), the top levels of a Merkle tree -- pays that floor.  Lanes of a warp are free when
+// the batch is small, so here a group of 8 lanes shares one state (BASELINE north_star: "one thread (or a
+// small cooperative group) per state").
+//
+// How: SIMT lanes must run the same instruction, so the work is cut into SLOTS of one Montgomery product
+// r = a*b/R per lane (fr.cuh dot_mont<1>, CIOS) with lane-dependent operands, glued by warp shuffles:
+//   * the state is REPLICATED in all 8 lanes of the group (canonical words), so operands are picked by lane
+//     index and nothing has to be routed before a slot;
+//   * partial round (gauged canonical form, hades.cuh partial_round_ccf): the S-box chain x^2, x^4, x^5 runs
+//     on lane 0 in slots 0..2; the 8 products of the two dot products (c_q.w and alpha_q.w) ride along in the
+//     other lanes (7 in slot 0, 1 in slot 1); their sums are formed by xor-butterflies while lane 0 is still
+//     squaring, so only "+ x^5, canonicalise" is left after slot 2: 3 products deep instead of 840/112 = 7.5;
+//   * full round: x^5 of the 5 words on lanes 0..4 (3 slots), then the 20 (25 in the last, dense round)
+//     matrix products in 3 (4) slots, each row summed by a butterfly over 4 lanes;
+//   * every product is reduced on its own (Montgomery reduction is linear), sums are taken on the reduced
+//     9-limb values and canonicalised once per output word.
+// Same tables as the one-thread canonical-form kernel (CcfLayout<5>), same F_p values, canonical outputs:
+// bit-identical results.  Per permutation: 59*3 + 7*6 + 7 + 2 = 228 slots of 112 products.
+//
+// `T::tab(entry, limb)` must accept a lane-dependent entry (the kernels copy the table to shared memory).
+// Shuffles go through coop_shfl / coop_shfl_xor: warp shuffles of width 8 on the device; in the host
+// emulation build (tests/host_emul) eight threads exchange through a barrier.
+#pragma once
+#include "hades.cuh"
+
+namespace hades {
+
+constexpr int kCoopLanes = 8;
+
+#if HADES_EMUL
+// provided by the emulation harness: lane id of the calling thread and the exchange primitives
+int coop_emul_lane();
+void coop_emul_exchange(uint32_t* v, int n, int src_lane_xor, int src_lane_abs);  // abs < 0: use xor
+inline void coop_shfl_xor_n(uint32_t* v, int n, int mask) { coop_emul_exchange(v, n, mask, -1); }
+inline void coop_shfl_n(uint32_t* v, int n, int src) { coop_emul_exchange(v, n, 0, src); }
+#else
+__device__ __forceinline__ void coop_shfl_xor_n(uint32_t* v, int n, int mask) {
+#pragma unroll
+    for (int k = 0; k < n; k++) v[k] = __shfl_xor_sync(0xffffffffu, v[k], mask, kCoopLanes);
+}
+__device__ __forceinline__ void coop_shfl_n(uint32_t* v, int n, int src) {
+#pragma unroll
+    for (int k = 0; k < n; k++) v[k] = __shfl_sync(0xffffffffu, v[k], src, kCoopLanes);
+}
+#endif
+
+// dst = cond ? a : dst  (per limb; SEL on the device)
+template <int N>
+HADES_DEV void coop_pick(uint32_t (&dst)[N], bool cond, const uint32_t (&a)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; k++) dst[k] = cond ? a[k] : dst[k];
+}
+
+// one slot: r = a*b/R mod p, 8 limbs, r < p + a*b/R (every product in this file has a < 1.96p and b < 1.96p, so
+// r < 2^256 and limb 8 is zero).  One CIOS stream (dot_mont<1>, 112 products).  Measured and rejected: splitting the
+// product into two independent carry-chain streams (low and high limbs of b reduced separately, 136 products) to
+// double the instruction-level parallelism -- a lone warp is NOT latency-bound but at ~57 % of the FMA pipe already
+// (ncu), so the extra products cost more than the parallelism buys: 166 us instead of 125 us per permutation
+// (profiles/r02_latency_coop_split_ab.txt).
+HADES_DEV void coop_mmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t t[9];
+    dot_mont<1>(t, [&](int, int k) { return a[k]; }, [&](int, int i) { return b[i]; });
+    HADES_ASSERT(t[8] == 0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = t[k];
+}
+
+// v (9 limbs) += a (8 limbs)
+HADES_DEV void coop_acc8(uint32_t (&v)[9], const uint32_t (&a)[8]) {
+    uint32_t lo[8], v8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v8[k] = v[k];
+    const uint32_t c = add8(lo, v8, a);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = lo[k];
+    v[8] += c;
+}
+// v (9 limbs) += a (9 limbs)
+HADES_DEV void coop_acc9(uint32_t (&v)[9], const uint32_t (&a)[9]) {
+    uint32_t a8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a8[k] = a[k];
+    coop_acc8(v, a8);
+    v[8] += a[8];
+}
+// v += v of lane (lane ^ mask)
+HADES_DEV void coop_butterfly(uint32_t (&v)[9], int mask) {
+    uint32_t o[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) o[k] = v[k];
+    coop_shfl_xor_n(o, 9, mask);
+    coop_acc9(v, o);
+}
+
+template <class T>
+HADES_DEV void coop_load_tab(uint32_t (&c)[8], int entry) {
+#if HADES_EMUL
+    for (int k = 0; k < 8; k++) c[k] = T::tab(entry, k);
+#else
+    const uint4* p = T::ptr4(entry);  // lane-dependent entry: two 128-bit shared-memory loads
+    const uint4 lo = p[0], hi = p[1];
+    c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w;
+    c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
+#endif
+}
+
+// word idx (lane-dependent, 0..N-1) of a replicated state
+template <int N>
+HADES_DEV void coop_select_word(uint32_t (&out)[8], const Fr (&s)[N], int idx) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[k] = s[0].l[k];
+#pragma unroll
+    for (int j = 1; j < N; j++) coop_pick(out, idx == j, s[j].l);
+}
+
+// x^5 of a canonical x, canonical result (three slots)
+HADES_DEV void coop_sbox(uint32_t (&x5)[8], const uint32_t (&x)[8]) {
+    uint32_t x2[8], x4[8];
+    coop_mmul(x2, x, x);     // < 1.453 p
+    coop_mmul(x4, x2, x2);   // < 1.956 p
+    coop_mmul(x5, x4, x);    // < 1.886 p
+    cond_sub_p8(x5);
+}
+
+// Rows of a matrix over a group of 4 lanes: lane (g, c) with g = lane >> 2, c = lane & 3 multiplies its operand
+// `b` (the same for both groups) by entry `e0 + row(g) * stride + c` and the four products plus `col0` (added by
+// c == 0) are summed by a butterfly.  Returns the canonical row in every lane of the group.
+// Bound: 4 products < 1.4528 p each (canonical operands) + col0 < 1.4528 p: < 7.3 p < 8 p.
+template <class T>
+HADES_DEV void coop_row_slot(Fr& out, int lane, int entry, bool active, const uint32_t (&b)[8], const uint32_t (&col0)[8]) {
+    uint32_t a[8], r[8], v[9];
+    coop_load_tab<T>(a, entry);
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = active ? a[k] : 0u;
+    coop_mmul(r, a, b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = r[k];
+    v[8] = 0;
+    uint32_t z[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) z[k] = ((lane & 3) == 0) ? col0[k] : 0u;
+    coop_acc8(v, z);
+    coop_butterfly(v, 1);
+    coop_butterfly(v, 2);
+    canon<2>(out, v);
+}
+
+// ARK + x^5 on all five words (lane j < 5 owns word j), then out = M * sbox: unit-column rows (full rounds 0..6:
+// out_i = s_0 + sum_{j>=1} tab[mat + 4 i + j - 1] s_j) or dense rows (last round: out_i = sum_j tab[mat + 5 i + j] s_j).
+template <class T, bool kDense>
+HADES_DEV void coop_full_round(Fr (&s)[5], int lane, int ark, int mat) {
+    const int widx = lane < 5 ? lane : 0;
+    uint32_t x[8], c[8], x5[8];
+    coop_select_word<5>(x, s, widx);
+    coop_load_tab<T>(c, ark + widx);
+    {
+        Fr xf, cf;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { xf.l[k] = x[k]; cf.l[k] = c[k]; }
+        fr_add(xf, xf, cf);
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = xf.l[k];
+    }
+    coop_sbox(x5, x);
+    // operand of the row slots: word (lane & 3) + 1; column-0 term: s_0 itself (unit column) or M[row][0] * s_0
+    uint32_t b[8], s0[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { b[k] = x5[k]; s0[k] = x5[k]; }
+    coop_shfl_n(b, 8, (lane & 3) + 1);
+    coop_shfl_n(s0, 8, 0);
+    const int c4 = lane & 3, g = lane >> 2;
+    uint32_t d[8];  // dense: lane i < 5 holds M[i][0] * s_0
+    if constexpr (kDense) {
+        uint32_t a[8];
+        coop_load_tab<T>(a, mat + 5 * widx);
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = lane < 5 ? a[k] : 0u;
+        coop_mmul(d, a, s0);
+    }
+    constexpr int kStride = kDense ? 5 : 4, kFirst = kDense ? 1 : 0;
+    Fr outA, outB, outC;
+    auto row = [&](Fr& out, int r) {
+        uint32_t col0[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) col0[k] = kDense ? d[k] : s0[k];
+        if constexpr (kDense) coop_shfl_n(col0, 8, r);
+        coop_row_slot<T>(out, lane, mat + kStride * r + kFirst + c4, true, b, col0);
+    };
+    row(outA, g);      // rows 0 | 1
+    row(outB, 2 + g);  // rows 2 | 3
+    row(outC, 4);      // row 4 in both groups
+    // replicate
+    Fr t;
+    t = outA; coop_shfl_n(t.l, 8, 0); s[0] = t;
+    t = outA; coop_shfl_n(t.l, 8, 4); s[1] = t;
+    t = outB; coop_shfl_n(t.l, 8, 0); s[2] = t;
+    t = outB; coop_shfl_n(t.l, 8, 4); s[3] = t;
+    s[4] = outC;
+}
+
+// partial round q (table entries base = {e, alpha[4], c[4]}): see the file header
+template <class T>
+HADES_DEV void coop_partial_round(Fr (&s)[5], int lane, int base) {
+    {
+        Fr e;
+#pragma unroll
+        for (int k = 0; k < 8; k++) e.l[k] = T::tab(base, k);
+        fr_add(s[4], s[4], e);
+    }
+    // slot 0: lane 0: x*x | lanes 1..3: c_j * w_j (j = lane - 1) | lanes 4..7: alpha_j * w_j (j = lane - 4)
+    const int j0 = lane == 0 ? 4 : (lane < 4 ? lane - 1 : lane - 4);
+    uint32_t a[8], b[8], r0[8], r1[8], r2[8];
+    coop_select_word<5>(b, s, j0);
+    coop_load_tab<T>(a, base + (lane < 4 ? 5 + j0 : 1 + j0));  // lane 0 reads a valid but unused entry
+    coop_pick(a, lane == 0, s[4].l);
+    coop_mmul(r0, a, b);
+    // slot 1: lane 0: x^2 * x^2 | lane 1: c_3 * w_3 | others idle
+    coop_load_tab<T>(a, base + 5 + 3);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = lane == 1 ? a[k] : 0u; b[k] = s[3].l[k]; }
+    coop_pick(a, lane == 0, r0);
+    coop_pick(b, lane == 0, r0);
+    coop_mmul(r1, a, b);
+    // sums of the reduced products (off the S-box chain): lanes 0..3 -> c . w, lanes 4..7 -> alpha . w
+    uint32_t v[9];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = lane == 0 ? 0u : r0[k];
+    v[8] = 0;
+    {
+        uint32_t z[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) z[k] = lane == 1 ? r1[k] : 0u;
+        coop_acc8(v, z);
+    }
+    coop_butterfly(v, 1);
+    coop_butterfly(v, 2);
+    uint32_t o[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) o[k] = v[k];
+    coop_shfl_xor_n(o, 9, 4);
+    uint32_t sc[9], sa[9];  // c . w and alpha . w (each < 4 * 1.4528 p), in every lane
+#pragma unroll
+    for (int k = 0; k < 9; k++) { sc[k] = lane < 4 ? v[k] : o[k]; sa[k] = lane < 4 ? o[k] : v[k]; }
+    // slot 2: lane 0: x^4 * x (others idle)
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = lane == 0 ? r1[k] : 0u; b[k] = s[4].l[k]; }
+    coop_mmul(r2, a, b);
+    coop_shfl_n(r2, 8, 0);  // y = x^5 / gauge, < 1.886 p, to every lane
+    coop_acc8(sc, r2);      // < 7.7 p
+    coop_acc8(sa, r2);
+    Fr newx, neww;
+    canon<2>(newx, sc);
+    canon<2>(neww, sa);
+#pragma unroll
+    for (int i = 0; i < 3; i++) s[i] = s[i + 1];
+    s[3] = neww;
+    s[4] = newx;
+}
+
+// back to the original basis after the partial rounds: z_i = w_0 + sum_{j=1..3} tab[pinv + 3 i + j - 1] w_j (i < 4)
+template <class T>
+HADES_DEV void coop_pinv_stage(Fr (&s)[5], int lane, int pinv) {
+    const int c4 = lane & 3, g = lane >> 2;
+    uint32_t b[8], w0[8];
+    coop_select_word<5>(b, s, c4);  // lane c4 = 0 multiplies nothing: its entry index below is clamped and masked
+#pragma unroll
+    for (int k = 0; k < 8; k++) w0[k] = s[0].l[k];
+    Fr outA, outB;
+    coop_row_slot<T>(outA, lane, pinv + 3 * g + (c4 ? c4 - 1 : 0), c4 != 0, b, w0);
+    coop_row_slot<T>(outB, lane, pinv + 3 * (2 + g) + (c4 ? c4 - 1 : 0), c4 != 0, b, w0);
+    Fr t;
+    t = outA; coop_shfl_n(t.l, 8, 0); s[0] = t;
+    t = outA; coop_shfl_n(t.l, 8, 4); s[1] = t;
+    t = outB; coop_shfl_n(t.l, 8, 0); s[2] = t;
+    t = outB; coop_shfl_n(t.l, 8, 4); s[3] = t;
+}
+
+// `Strategy::perm` (src/strategies.rs:140-157) on the replicated state of one 8-lane group
+template <class T>
+HADES_DEV void hades_perm_coop(Fr (&s)[5], int lane) {
+    typedef CcfLayout<5> L;
+    constexpr int kHalf = kFullRounds / 2;
+#if !HADES_EMUL
+#pragma unroll 1
+#endif
+    for (int f = 0; f + 1 < kFullRounds; f++) {
+        coop_full_round<T, false>(s, lane, L::kArk + f * 5, L::kMat + f * L::kMatStride);
+        if (f == kHalf - 1) {
+            add_table_vector<5, T>(s, L::kC4);
+#if !HADES_EMUL
+#pragma unroll 1
+#endif
+            for (int q = 0; q < kPartialRounds; q++) coop_partial_round<T>(s, lane, L::kPart + q * L::kPartStride);
+            coop_pinv_stage<T>(s, lane, L::kPinv);
+        }
+    }
+    coop_full_round<T, true>(s, lane, L::kArk + (kFullRounds - 1) * 5, L::kLast);
+}
+
+}  // namespace hades

@@ -28,6 +28,11 @@ namespace {
 constexpr int kRounds = 67;                      // 8 full + 59 partial (src/lib.rs:20-27)
 constexpr int kNumBuf = 3;                       // chunk buffers (and streams) per device
 constexpr size_t kChunkBytes = (size_t)96 << 20;  // target bytes per pipeline chunk
+// Batches / Merkle levels up to this many states run the cooperative 8-lanes-per-state kernels (coop.cuh): below it
+// the one-thread-per-state kernel is latency-bound (one warp per scheduler, ~270 us whatever the size).
+// Measured (profiles/r02_latency_small_batches.txt): 127 us up to 2368 states (one 16-state block per SM), 178 us up to
+// 4736, 333 us at 8192 -- against 269 us for the one-thread kernel at any size up to 16 384.
+constexpr int kDefaultCoopMax = 4736;
 
 struct DeviceState {
     int ordinal = 0;
@@ -185,7 +190,10 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
         if (rc == HADES_OK) {
             ctx->has_ccf = hades_host::derive_tables_ccf((int)width, ark_limbs, mds_limbs, ccf) && ccf.size() == ctx->ops2[2]->table_u64;
             if (!ctx->has_ccf) ccf.clear();
-            else ctx->variant.algo = 2;
+            else {
+                ctx->variant.algo = 2;
+                if (width == 5) ctx->variant.coop_max = kDefaultCoopMax;
+            }
         }
     }
     for (int g = 0; g < n_dev && rc == HADES_OK; g++) {
@@ -671,7 +679,16 @@ int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
     if (!ctx || algo < 0 || algo > 2 || regs < 0 || regs > 10) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     if (ctx->generic()) return fail(ctx, HADES_ERR_INVALID_ARG, "width %u runs the generic kernel, which has no variants", ctx->width);
     if (algo == 2 && !ctx->has_ccf) return fail(ctx, HADES_ERR_CONSTANTS, "the canonical-form schedule could not be derived for these constants");
-    ctx->variant = Variant{algo, regs};
+    ctx->variant.algo = algo;
+    ctx->variant.regs = regs;
+    return HADES_OK;
+}
+
+int hades_set_coop_threshold(hades_ctx* ctx, size_t max_states) {
+    if (!ctx) return fail(ctx, HADES_ERR_INVALID_ARG, "null context");
+    if (ctx->width != 5 || !ctx->has_ccf)
+        return fail(ctx, HADES_ERR_INVALID_ARG, "the cooperative kernels exist for width 5 with the canonical-form tables only");
+    ctx->variant.coop_max = (int)std::min<size_t>(max_states, (size_t)1 << 24);
     return HADES_OK;
 }
 

@@ -9,6 +9,9 @@
 #include <string.h>
 
 #include "hades.cuh"
+#if HADES_W == 5 && HADES_ALGO == 2
+#include "coop.cuh"
+#endif
 #include "width_ops.hpp"
 
 namespace hades {
@@ -335,10 +338,78 @@ sponge_lockstep_kernel(const uint4* __restrict__ elems, const uint64_t* __restri
 #endif  // HADES_ALGO >= 1
 #endif  // HADES_W == 5
 
+
+#if HADES_W == 5 && HADES_ALGO == 2
+// ---- cooperative small-batch kernels (coop.cuh): one state per 8 lanes, table staged in shared memory ---------
+// The lanes of a group read DIFFERENT table entries in the same instruction, which the constant cache would
+// serialise; the 24 KB canonical-form table is therefore mirrored in global memory (uploaded with the constant
+// bank) and copied to shared memory by every block.
+__device__ uint4 g_coop_table[kTableEntries * 2];
+extern __shared__ __align__(16) uint32_t coop_smem[];
+struct CoopTab {
+    static __device__ __forceinline__ uint32_t tab(int entry, int k) { return coop_smem[entry * 8 + k]; }
+    static __device__ __forceinline__ const uint4* ptr4(int entry) { return reinterpret_cast<const uint4*>(coop_smem) + entry * 2; }
+};
+constexpr int kCoopBlock = 128;                        // 16 states per block, one warp per scheduler
+constexpr int kCoopStatesPerBlock = kCoopBlock / kCoopLanes;
+constexpr size_t kCoopSmemBytes = (size_t)kTableEntries * 32;
+static_assert(kCoopSmemBytes <= 48 * 1024, "table must fit the default dynamic shared memory limit");
+
+__device__ __forceinline__ void coop_stage_table() {
+    uint4* dst = reinterpret_cast<uint4*>(coop_smem);
+    for (int i = threadIdx.x; i < kTableEntries * 2; i += kCoopBlock) dst[i] = g_coop_table[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCoopBlock) perm_batch_coop_kernel(uint4* __restrict__ states, size_t n) {
+    coop_stage_table();
+    const int lane = threadIdx.x & (kCoopLanes - 1);
+    const size_t g = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const bool live = g < n;
+    Fr s[5];
+    const uint4* p = states + (live ? g : 0) * 10;  // all lanes of the group read the same 160 bytes (broadcast)
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        if (live) fr_load(s[j], p + 2 * j);
+        else fr_set_zero(s[j]);
+    }
+    hades_perm_coop<CoopTab>(s, lane);
+    if (live && lane < 5) {  // lane j writes word j
+        Fr w;
+        coop_select_word<5>(w.l, s, lane);
+        fr_store(states + g * 10 + 2 * lane, w);
+    }
+}
+
+__global__ void __launch_bounds__(kCoopBlock)
+merkle_level_coop_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out, size_t n_in) {
+    coop_stage_table();
+    const int lane = threadIdx.x & (kCoopLanes - 1);
+    const size_t g = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const bool live = g < n_out;
+    const size_t first_child = 4 * (live ? g : 0);
+    const int present = !live ? 0 : (n_in - first_child < 4 ? (int)(n_in - first_child) : 4);
+    Fr s[5];
+    fr_set_mask(s[0], present);
+    const uint4* p = in + first_child * 2;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (j < present) fr_load(s[1 + j], p + 2 * j);
+        else fr_set_zero(s[1 + j]);
+    }
+    hades_perm_coop<CoopTab>(s, lane);
+    if (live && lane == 0) fr_store(out + g * 2, s[1]);
+}
+#endif  // cooperative kernels
+
 // ---- host-side launchers ---------------------------------------------------------------------------
 cudaError_t upload(const uint64_t* table) {
     cudaError_t e = upload_modulus();
     if (e != cudaSuccess) return e;
+#if HADES_W == 5 && HADES_ALGO == 2
+    e = cudaMemcpyToSymbol(g_coop_table, table, sizeof(c_table), 0, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+#endif
     return cudaMemcpyToSymbol(c_table, table, sizeof(c_table), 0, cudaMemcpyHostToDevice);
 }
 
@@ -355,6 +426,13 @@ cudaError_t upload(const uint64_t* table) {
 
 cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
+#if HADES_W == 5 && HADES_ALGO == 2
+    if (n <= (size_t)v.coop_max) {  // small batch: 8 lanes per state (latency kernel)
+        const unsigned blocks = (unsigned)((n + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
+        perm_batch_coop_kernel<<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(reinterpret_cast<uint4*>(d_states), n);
+        return cudaGetLastError();
+    }
+#endif
 #if HADES_ALGO >= 1
     if (v.regs >= 4) {  // lockstep launches: regs 4 -> 256 threads per block, 5 -> 512, 6.. experimental
         uint4* p = reinterpret_cast<uint4*>(d_states);
@@ -392,6 +470,14 @@ cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s)
 cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, size_t n_in, cudaStream_t s) {
     if (n_out == 0) return cudaSuccess;
     if (n_in > 4 * n_out || n_in + 3 < 4 * n_out) return cudaErrorInvalidValue;  // n_out == ceil(n_in / 4)
+#if HADES_ALGO == 2
+    if (n_out <= (size_t)v.coop_max) {  // small level: 8 lanes per node (latency kernel)
+        const unsigned blocks = (unsigned)((n_out + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
+        merkle_level_coop_kernel<<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(
+            reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out, n_in);
+        return cudaGetLastError();
+    }
+#endif
 #if HADES_ALGO >= 1
     if (v.regs >= 4) {  // lockstep launch shapes share one Merkle build
         merkle_level_lockstep_kernel<128, 5><<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(
@@ -435,6 +521,10 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
                      : cudaFuncGetAttributes(out, KERNEL<kAlgo, 5>))
 
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
+#if HADES_W == 5 && HADES_ALGO == 2
+    if (!strcmp(kernel, "perm_coop")) return cudaFuncGetAttributes(out, perm_batch_coop_kernel);
+    if (!strcmp(kernel, "merkle_coop")) return cudaFuncGetAttributes(out, merkle_level_coop_kernel);
+#endif
 #if HADES_ALGO >= 1
     if (!strcmp(kernel, "perm") && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);
     if (!strcmp(kernel, "perm") && v.regs == 5) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<512, 1>);

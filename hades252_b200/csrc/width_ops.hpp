@@ -20,6 +20,9 @@ namespace hades {
 struct Variant {
     int algo;
     int regs;
+    // Batches (and Merkle levels) of at most this many states run the cooperative 8-lanes-per-state kernels
+    // (coop.cuh; width 5, algo 2 only); 0 disables them.  hades_set_coop_threshold.
+    int coop_max = 0;
 };
 constexpr int kPermThreads = 128;
 

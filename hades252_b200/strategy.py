@@ -200,6 +200,11 @@ class CudaStrategy(Strategy):
         (default); regs = launch shape (include/hades_cuda.h; 6 = lockstep 128-thread blocks, the default at W = 3, 5)."""
         self._check(self._lib.hades_set_variant(self._ctx, algo, regs))
 
+    def set_coop_threshold(self, max_states: int) -> None:
+        """Batches / Merkle levels of at most `max_states` states use the cooperative 8-lanes-per-state kernels
+        (width 5, algo 2; 0 disables; bit-identical results)."""
+        self._check(self._lib.hades_set_coop_threshold(self._ctx, max_states))
+
     def host_register(self, ptr: int, nbytes: int) -> None:
         self._check(self._lib.hades_host_register(self._ctx, ptr, nbytes))
 

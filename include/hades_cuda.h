@@ -168,6 +168,11 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
  * with at most 128/168/255/96 registers per thread, 4/5 = lockstep blocks of 256/512 threads, 6.. = lockstep
  * 128-thread blocks (the default; see hades252_b200/csrc/width_ops.hpp). */
 int hades_set_variant(hades_ctx* ctx, int algo, int regs);
+/* Small-batch path: batches (and Merkle levels) of at most `max_states` states run the cooperative kernels --
+ * one state per group of 8 lanes, 2.1x lower latency (125 us) than the one-thread-per-state kernel, which is
+ * latency-bound below ~2^14 states (a lone `Strategy::perm`, strategies.rs:140, is a batch of one).  Width 5,
+ * algo 2 only; 0 disables; default 4736 (two 16-state blocks per SM).  Results are bit-identical either way. */
+int hades_set_coop_threshold(hades_ctx* ctx, size_t max_states);
 /* Number of kernel launches issued through this context since creation (bench's gpu_launches). */
 uint64_t hades_launch_count(const hades_ctx* ctx);
 

@@ -6,7 +6,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <pthread.h>
+#include <thread>
 #include "../../hades252_b200/csrc/hades.cuh"
+#include "../../hades252_b200/csrc/coop.cuh"
 #include "../../hades252_b200/csrc/host_tables.hpp"
 
 extern "C" {
@@ -80,6 +83,52 @@ static int check_perm(int iters) {
     return 0;
 }
 
+// ---- cooperative kernel (coop.cuh): 8 host threads play the 8 lanes of a group; a shuffle is an exchange
+// through a shared array between two barriers
+static pthread_barrier_t g_bar;
+static uint32_t g_xchg[8][16];
+static thread_local int tl_lane;
+namespace hades {
+int coop_emul_lane() { return tl_lane; }
+void coop_emul_exchange(uint32_t* v, int n, int xmask, int abs_src) {
+    memcpy(g_xchg[tl_lane], v, 4 * n);
+    pthread_barrier_wait(&g_bar);
+    const int src = abs_src >= 0 ? abs_src : (tl_lane ^ xmask);
+    uint32_t tmp[16];
+    memcpy(tmp, g_xchg[src], 4 * n);
+    pthread_barrier_wait(&g_bar);
+    memcpy(v, tmp, 4 * n);
+}
+}  // namespace hades
+
+static int check_coop(int iters) {
+    pthread_barrier_init(&g_bar, nullptr, 8);
+    for (int it = 0; it < iters; it++) {
+        uint64_t st[20];
+        for (int j = 0; j < 5; j++) rand_fr(st + 4 * j, it < 40 ? (it + j) % 5 : 0);
+        hades::Fr s0[5], res[8][5];
+        for (int j = 0; j < 5; j++) to32(s0[j], st + 4 * j);
+        std::thread th[8];
+        for (int l = 0; l < 8; l++)
+            th[l] = std::thread([&, l]() {
+                tl_lane = l;
+                hades::Fr s[5];
+                for (int j = 0; j < 5; j++) s[j] = s0[j];
+                hades::hades_perm_coop<HostTabCcf<5>>(s, l);
+                for (int j = 0; j < 5; j++) res[l][j] = s[j];
+            });
+        for (int l = 0; l < 8; l++) th[l].join();
+        oracle_perm(st, 5, g_ark.data(), g_mds[5].data());
+        for (int l = 0; l < 8; l++)
+            for (int j = 0; j < 5; j++) {
+                uint64_t got[4]; to64(got, res[l][j]);
+                if (memcmp(got, st + 4 * j, 32)) { printf("perm_coop mismatch iter %d lane %d word %d\n", it, l, j); return 1; }
+            }
+    }
+    pthread_barrier_destroy(&g_bar);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     FILE* f = fopen(argv[1], "rb");
@@ -133,6 +182,7 @@ int main(int argc, char** argv) {
         if (memcmp(got, want, 32)) { printf("sqr mismatch %d\n", it); return 1; }
     }
     if (check_perm<5>(300) || check_perm<3>(100) || check_perm<9>(60)) return 1;
+    if (check_coop(80)) return 1;
     printf("host emulation OK\n");
     return 0;
 }

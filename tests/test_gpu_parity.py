@@ -516,3 +516,59 @@ def test_merkle_tree_single_leaf_and_errors(cuda_strategy, oracle):
     assert cuda_strategy.merkle_tree_nodes(1) == 0
     with pytest.raises(HadesError):
         cuda_strategy.merkle_root_ragged(np.empty((0, 4), dtype=np.uint64))
+
+
+# ---- cooperative small-batch kernels (coop.cuh): one state per 8 lanes ------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 63, 64, 65, 1000, 4735, 4736])
+def test_coop_perm_bit_identical(oracle, n):
+    """Batches at or below the cooperative threshold run perm_batch_coop_kernel; same bits as the oracle and as
+    the one-thread-per-state kernel (threshold 0)."""
+    import torch
+    from hades252_b200 import CudaStrategy
+    s = oracle.gen_elems(1234 + n, 5 * n).reshape(n, 5, 4)
+    want = oracle.perm_batch(s)
+    with CudaStrategy([0]) as strat:
+        assert strat.kernel_info("perm_coop")["local_bytes"] == 0
+        strat.set_coop_threshold(1 << 20)
+        l0 = strat.launch_count
+        d = torch.from_numpy(s.view(np.int64).copy()).cuda()
+        strat.perm_batch_device(d.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert strat.launch_count == l0 + 1
+        assert np.array_equal(d.cpu().numpy().view(np.uint64).reshape(n, 5, 4), want)
+        got = s.copy()
+        strat.perm_batch(got)          # host path, small batch -> one cooperative launch
+        assert np.array_equal(got, want)
+        strat.set_coop_threshold(0)
+        got = s.copy()
+        strat.perm_batch(got)
+        assert np.array_equal(got, want)
+
+
+def test_coop_single_perm_and_edge_values(oracle, H):
+    """`Strategy::perm` (a batch of one) goes through the cooperative kernel by default; edge operands."""
+    from hades252_b200 import CudaStrategy
+    P = H.P
+    vals = [0, 1, P - 1, P - 2, H.R, (1 << 255) % P, (1 << 64) - 1, P >> 1]
+    with CudaStrategy([0]) as strat:
+        for k in range(len(vals)):
+            st = np.array([H.to_mont_limbs(vals[(k + j) % len(vals)]) for j in range(5)], dtype=np.uint64)
+            want = oracle.perm_batch(st[None])[0]
+            strat.perm(st)
+            assert np.array_equal(st, want)
+
+
+@pytest.mark.parametrize("n", [4 ** 6, 3 * 4 ** 5 + 77, 13])
+def test_coop_merkle_levels(oracle, n):
+    """every level of the tree through merkle_level_coop_kernel (threshold above the leaf count), ragged tails
+    included; root equals the oracle's and the one-thread kernel's"""
+    from hades252_b200 import CudaStrategy
+    leaves = oracle.gen_elems(4321 + n, n)
+    want = oracle.merkle_tree(leaves)[-1]
+    with CudaStrategy([0]) as strat:
+        strat.set_coop_threshold(1 << 20)
+        assert np.array_equal(strat.merkle_root_ragged(leaves), want)
+        if n == 4 ** 6:
+            assert np.array_equal(strat.merkle_root(leaves), want)
+        strat.set_coop_threshold(0)
+        assert np.array_equal(strat.merkle_root_ragged(leaves), want)
