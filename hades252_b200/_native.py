@@ -33,6 +33,13 @@ SIGNATURES = {
     "hades_sponge_batch": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "hades_sponge_batch_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                               ctypes.c_void_p, ctypes.c_void_p]),
+    "hades_sponge_batch_ds": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, u64p, ctypes.c_void_p]),
+    "hades_sponge_batch_ds_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                 u64p, ctypes.c_void_p, ctypes.c_void_p]),
+    "hades_collective": (ctypes.c_char_p, [ctx_p]),
+    "hades_copy_probe": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "hades_set_host_path": (ctypes.c_int, [ctx_p, ctypes.c_int]),
+    "hades_last_host_path": (ctypes.c_char_p, [ctx_p]),
     "hades_host_register": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_size_t]),
     "hades_host_unregister": (ctypes.c_int, [ctx_p, ctypes.c_void_p]),
     "hades_gen_elems_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t,

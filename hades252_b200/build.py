@@ -76,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if (os.path.exists(LIB) and all(getattr(r[3], "fresh", False) for r in results)
             and all(os.path.getmtime(r[1]) <= os.path.getmtime(LIB) for r in results)):
         return LIB
-    link = [nvcc, "-shared", "-cudart", "static", "-o", LIB, *[r[1] for r in results]]
+    link = [nvcc, "-shared", "-cudart", "static", "-o", LIB, *[r[1] for r in results], "-ldl", "-lpthread"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(log, "a") as f:
         f.write(" ".join(link) + "\n" + res.stdout)

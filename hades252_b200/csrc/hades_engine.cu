@@ -6,13 +6,21 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hades_cuda.h"
@@ -26,7 +34,7 @@ using namespace hades;
 namespace {
 
 constexpr int kRounds = 67;                      // 8 full + 59 partial (src/lib.rs:20-27)
-constexpr int kNumBuf = 3;                       // chunk buffers (and streams) per device
+constexpr int kNumBuf = 4;                       // chunk buffers (and streams) per device
 constexpr size_t kChunkBytes = (size_t)96 << 20;  // target bytes per pipeline chunk
 // Batches / Merkle levels up to this many states run the cooperative 8-lanes-per-state kernels (coop.cuh): below it
 // the one-thread-per-state kernel is latency-bound (one warp per scheduler, ~270 us whatever the size).
@@ -37,9 +45,116 @@ constexpr int kDefaultCoopMax = 4736;
 struct DeviceState {
     int ordinal = 0;
     uint64_t* generic_tables = nullptr;  // widths without a tuned kernel: ark ++ mds in global memory
-    cudaStream_t streams[kNumBuf] = {nullptr, nullptr, nullptr};
-    uint64_t* chunk[kNumBuf] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[kNumBuf] = {};
+    uint64_t* chunk[kNumBuf] = {};       // device chunk buffers of the host pipeline (grow-only)
     size_t chunk_bytes = 0;
+    uint64_t* bounce[kNumBuf] = {};      // pinned staging buffers for PAGEABLE caller memory (grow-only)
+    size_t bounce_bytes = 0;
+    cudaEvent_t done[kNumBuf] = {};      // chunk b's D2H has landed in bounce[b]
+    uint64_t* work = nullptr;            // persistent scratch of the Merkle / sponge host paths (grow-only)
+    size_t work_bytes = 0;
+    ncclComm_t comm = nullptr;           // rank of this device in the context's communicator (n_dev > 1)
+};
+
+// ---- NCCL, loaded on demand (single-device contexts never touch it) ------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool ok() const { return handle != nullptr; }
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // the soname every NCCL 2.x ships; a process that already loaded one (e.g. torch's bundled copy) gets that one
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { api.error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return; }
+        bool all = true;
+        auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p) { all = false; api.error = std::string("missing symbol ") + name; } return p; };
+        api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        if (all) api.handle = h;
+    });
+    return api;
+}
+
+// ---- host copy pool: slices of user<->pinned copies for the pageable pipeline ----------------------------------
+class CopyPool {
+  public:
+    static CopyPool& get() { static CopyPool p; return p; }
+    // dst <- src, split over the workers; returns when every byte has been copied
+    void copy(void* dst, const void* src, size_t bytes) {
+        const size_t kSlice = (size_t)4 << 20;
+        const size_t n = std::max<size_t>(1, std::min<size_t>(workers_.size(), (bytes + kSlice - 1) / kSlice));
+        if (n == 1 || workers_.empty()) { memcpy(dst, src, bytes); return; }
+        struct Job { std::atomic<size_t> left; std::mutex m; std::condition_variable cv; } job;
+        job.left = n;
+        const size_t per = ((bytes + n - 1) / n + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (size_t i = 0; i < n; i++) {
+                const size_t off = std::min(bytes, i * per), len = std::min(per, bytes - off);
+                q_.push_back([=, &job] {
+                    if (len) memcpy((char*)dst + off, (const char*)src + off, len);
+                    if (job.left.fetch_sub(1) == 1) { std::lock_guard<std::mutex> l2(job.m); job.cv.notify_all(); }
+                });
+            }
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(job.m);
+        job.cv.wait(lk, [&] { return job.left.load() == 0; });
+    }
+    size_t threads() const { return workers_.size(); }
+
+  private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        if (const char* e = getenv("HADES_COPY_THREADS")) hw = (unsigned)std::max(0, atoi(e));
+        const unsigned n = std::min(16u, hw);
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> workers_;
+    bool stop_ = false;
+};
+
+// every entry point leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 thread_local std::string g_init_error;
@@ -52,10 +167,16 @@ struct hades_ctx {
     const WidthOps* ops() const { return ops2[variant.algo]; }
     bool generic() const { return ops2[0] == nullptr; }  // no tuned kernel for this width
     Variant variant = {1, 0};  // optimised schedule, <=128 registers
+    bool has_sparse = false;   // sparse partial-round tables derived (algo 1 available)
     bool has_ccf = false;      // canonical-form tables derived (algo 2 available)
     std::vector<DeviceState> devs;
     mutable std::string err;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
+    bool use_nccl = false;     // communicator over all devices of the context (n_dev > 1, distinct ordinals)
+    std::string collective = "none (single device)";
+    bool probe = false;        // hades_copy_probe: run the host pipeline without the kernel
+    bool force_bounce = false, force_direct = false;  // hades_set_host_path (tests / A-B)
+    std::string last_host_path = "none";
 };
 
 namespace {
@@ -70,6 +191,8 @@ int fail(hades_ctx* ctx, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
+    static std::mutex err_mutex;  // device pipelines of one call may fail concurrently
+    std::lock_guard<std::mutex> lk(err_mutex);
     if (ctx) ctx->err = buf;
     else g_init_error = buf;
     return code;
@@ -98,7 +221,7 @@ int upload_tables(hades_ctx* ctx, int ordinal, const std::vector<uint64_t>& dens
         return HADES_OK;
     }
     CUDA_TRY(ctx, ctx->ops2[0]->upload(dense.data()));
-    CUDA_TRY(ctx, ctx->ops2[1]->upload(opt.data()));
+    if (!opt.empty()) CUDA_TRY(ctx, ctx->ops2[1]->upload(opt.data()));
     if (!ccf.empty()) CUDA_TRY(ctx, ctx->ops2[2]->upload(ccf.data()));
     g_tables[{ordinal, (int)ctx->width}] = dense;
     return HADES_OK;
@@ -116,6 +239,7 @@ int launch_perm_w(hades_ctx* ctx, uint64_t* d_states, size_t n, cudaStream_t str
     return HADES_OK;
 }
 
+// grow-only device / pinned buffers owned by the context (the current device must be d.ordinal)
 int ensure_chunks(hades_ctx* ctx, DeviceState& d, size_t bytes) {
     if (d.chunk_bytes >= bytes) return HADES_OK;
     for (int b = 0; b < kNumBuf; b++) {
@@ -125,6 +249,27 @@ int ensure_chunks(hades_ctx* ctx, DeviceState& d, size_t bytes) {
     d.chunk_bytes = 0;
     for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaMalloc(&d.chunk[b], bytes));
     d.chunk_bytes = bytes;
+    return HADES_OK;
+}
+int ensure_bounce(hades_ctx* ctx, DeviceState& d, size_t bytes) {
+    if (d.bounce_bytes >= bytes) return HADES_OK;
+    for (int b = 0; b < kNumBuf; b++) {
+        if (d.bounce[b]) CUDA_TRY(ctx, cudaFreeHost(d.bounce[b]));
+        d.bounce[b] = nullptr;
+    }
+    d.bounce_bytes = 0;
+    for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaHostAlloc(&d.bounce[b], bytes, cudaHostAllocPortable));
+    d.bounce_bytes = bytes;
+    return HADES_OK;
+}
+int ensure_work(hades_ctx* ctx, DeviceState& d, size_t bytes) {
+    if (d.work_bytes >= bytes) return HADES_OK;
+    if (d.work) CUDA_TRY(ctx, cudaFree(d.work));
+    d.work = nullptr;
+    d.work_bytes = 0;
+    bytes = (bytes + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+    CUDA_TRY(ctx, cudaMalloc(&d.work, bytes));
+    d.work_bytes = bytes;
     return HADES_OK;
 }
 
@@ -152,6 +297,114 @@ int log4_exact(size_t n) {  // k if n == 4^k else -1
     return (lg & 1) ? -1 : lg / 2;
 }
 
+#define NCCL_TRY(ctx, expr)                                                                               \
+    do {                                                                                                  \
+        ncclResult_t r_ = (expr);                                                                         \
+        if (r_ != ncclSuccess)                                                                            \
+            return fail(ctx, HADES_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, nccl_api().GetErrorString(r_), \
+                        __FILE__, __LINE__);                                                              \
+    } while (0)
+
+// One communicator rank per device of the context (single process: ncclCommInitAll).  Without NCCL (library not
+// found) or with a device listed twice (NCCL needs distinct devices) the subtree roots travel by direct peer copies.
+void init_collective(hades_ctx* ctx) {
+    const int G = (int)ctx->devs.size();
+    if (G < 2) return;
+    std::vector<int> ords;
+    for (auto& d : ctx->devs) ords.push_back(d.ordinal);
+    std::vector<int> sorted = ords;
+    std::sort(sorted.begin(), sorted.end());
+    if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) {
+        ctx->collective = "peer copies (cudaMemcpyPeerAsync): a device is listed twice, NCCL needs distinct devices";
+        return;
+    }
+    NcclApi& api = nccl_api();
+    if (!api.ok()) {
+        ctx->collective = "peer copies (cudaMemcpyPeerAsync): " + api.error;
+        return;
+    }
+    std::vector<ncclComm_t> comms(G, nullptr);
+    ncclResult_t r = api.CommInitAll(comms.data(), G, ords.data());
+    if (r != ncclSuccess) {
+        ctx->collective = std::string("peer copies (cudaMemcpyPeerAsync): ncclCommInitAll failed: ") + api.GetErrorString(r);
+        return;
+    }
+    for (int g = 0; g < G; g++) ctx->devs[g].comm = comms[g];
+    int ver = 0;
+    api.GetVersion(&ver);
+    char buf[96];
+    snprintf(buf, sizeof buf, "ncclAllGather (NCCL %d.%d.%d, ncclCommInitAll over %d devices)", ver / 10000, (ver / 100) % 100, ver % 100, G);
+    ctx->collective = buf;
+    ctx->use_nccl = true;
+}
+
+// ---- host pipeline of hades_perm_batch on ONE device: states [lo, hi) of the caller's buffer -------------------
+// bounce: the caller's memory is PAGEABLE (a Rust `&mut [[BlsScalar; WIDTH]]`, a numpy array).  cudaMemcpyAsync from
+// pageable memory is synchronous and staged by the driver on the calling thread, so the chunks are staged here
+// instead: the copy pool fills pinned buffer b from the caller's memory, the stream does H2D -> kernel -> D2H in
+// place, and a drainer thread copies the results back while the next chunks are in flight.
+int pipeline_bounce(hades_ctx* ctx, DeviceState& d, uint64_t* host_states, size_t lo, size_t hi, size_t chunk_states) {
+    const size_t state_bytes = (size_t)ctx->width * 32;
+    const size_t n_chunks = (hi - lo + chunk_states - 1) / chunk_states;
+    std::mutex m;
+    std::condition_variable cv;
+    size_t issued = 0, drained = 0;  // chunks handed to the stream / copied back to the caller
+    bool failed = false;
+    cudaError_t drain_err = cudaSuccess;
+    std::thread drainer([&] {
+        cudaSetDevice(d.ordinal);
+        for (size_t c = 0; c < n_chunks; c++) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return issued > c || failed; });
+                if (issued <= c) return;
+            }
+            const int b = (int)(c % kNumBuf);
+            cudaError_t e = cudaEventSynchronize(d.done[b]);
+            const size_t at = lo + c * chunk_states, cnt = std::min(chunk_states, hi - at);
+            if (e == cudaSuccess) CopyPool::get().copy(host_states + at * ctx->width * 4, d.bounce[b], cnt * state_bytes);
+            std::lock_guard<std::mutex> lk(m);
+            if (e != cudaSuccess) { drain_err = e; failed = true; }
+            drained = c + 1;
+            cv.notify_all();
+        }
+    });
+    int rc = HADES_OK;
+    auto body = [&]() -> int {
+        for (size_t c = 0; c < n_chunks; c++) {
+            const int b = (int)(c % kNumBuf);
+            {
+                std::unique_lock<std::mutex> lk(m);  // buffer b is free once chunk c - kNumBuf has been drained
+                cv.wait(lk, [&] { return c < kNumBuf || drained + kNumBuf > c || failed; });
+                if (failed) return HADES_OK;
+            }
+            const size_t at = lo + c * chunk_states, cnt = std::min(chunk_states, hi - at);
+            CopyPool::get().copy(d.bounce[b], host_states + at * ctx->width * 4, cnt * state_bytes);
+            CUDA_TRY(ctx, cudaMemcpyAsync(d.chunk[b], d.bounce[b], cnt * state_bytes, cudaMemcpyHostToDevice, d.streams[b]));
+            if (!ctx->probe) {
+                int r = launch_perm_w(ctx, d.chunk[b], cnt, d.streams[b], &d);
+                if (r) return r;
+            }
+            CUDA_TRY(ctx, cudaMemcpyAsync(d.bounce[b], d.chunk[b], cnt * state_bytes, cudaMemcpyDeviceToHost, d.streams[b]));
+            CUDA_TRY(ctx, cudaEventRecord(d.done[b], d.streams[b]));
+            std::lock_guard<std::mutex> lk(m);
+            issued = c + 1;
+            cv.notify_all();
+        }
+        return HADES_OK;
+    };
+    rc = body();
+    {
+        std::lock_guard<std::mutex> lk(m);
+        if (rc != HADES_OK) failed = true;
+        cv.notify_all();
+    }
+    drainer.join();
+    if (rc == HADES_OK && drain_err != cudaSuccess)
+        rc = fail(ctx, HADES_ERR_CUDA, "perm_batch pipeline failed on device %d: %s", d.ordinal, cudaGetErrorString(drain_err));
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -172,27 +425,32 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
     if (e != cudaSuccess || count < 1)
         return fail(nullptr, HADES_ERR_NO_DEVICE, "no CUDA device available (%s); this engine has no CPU fallback",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    DeviceGuard guard;
     hades_ctx* ctx = new hades_ctx();
     ctx->width = width;
     if (tuned)
         for (int a = 0; a < 3; a++) ctx->ops2[a] = width == 3 ? width_ops_3(a) : width == 5 ? width_ops_5(a) : width_ops_9(a);
-    ctx->variant = Variant{1, width == 9 ? 7 : 6};  // lockstep 128-thread blocks: x7 (W=3), x5 (W=5), x3 (W=9) per SM
+    ctx->variant.algo = 0;
+    ctx->variant.regs = 0;
     // dense table = ROUND_CONSTANTS[0..67W) ++ MDS_MATRIX; optimised table derived from it (host_tables.hpp)
     std::vector<uint64_t> dense(ark_limbs, ark_limbs + (size_t)kRounds * width * 4), opt, ccf;
     dense.insert(dense.end(), mds_limbs, mds_limbs + (size_t)width * width * 4);
     int rc = HADES_OK;
     if (tuned) {
         if (dense.size() != ctx->ops2[0]->table_u64) rc = fail(nullptr, HADES_ERR_INVALID_ARG, "internal: dense table size");
-        if (rc == HADES_OK && (!hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) || opt.size() != ctx->ops2[1]->table_u64))
-            rc = fail(nullptr, HADES_ERR_CONSTANTS, "could not derive the sparse partial-round tables (singular MDS sub-matrix)");
-        // The gauged canonical-form schedule (default) needs a controllable MDS block and non-zero pivots; with
-        // constants where that fails (never with the reference's assets) the sparse schedule stays the default.
+        // Schedules, best first: gauged canonical form (needs a controllable MDS block and non-zero pivots), sparse
+        // partial rounds (needs invertible MDS sub-matrices), dense (the reference's round structure, always
+        // available).  With the reference's assets all three derive; with custom constants where a derivation
+        // fails the next one becomes the default -- the dense schedule needs no derived table at all.
         if (rc == HADES_OK) {
+            ctx->has_sparse = hades_host::derive_tables((int)width, ark_limbs, mds_limbs, opt) && opt.size() == ctx->ops2[1]->table_u64;
+            if (!ctx->has_sparse) opt.clear();
             ctx->has_ccf = hades_host::derive_tables_ccf((int)width, ark_limbs, mds_limbs, ccf) && ccf.size() == ctx->ops2[2]->table_u64;
             if (!ctx->has_ccf) ccf.clear();
-            else {
-                ctx->variant.algo = 2;
-                if (width == 5) ctx->variant.coop_max = kDefaultCoopMax;
+            if (ctx->has_sparse || ctx->has_ccf) {
+                ctx->variant.algo = ctx->has_ccf ? 2 : 1;
+                ctx->variant.regs = width == 9 ? 7 : 6;  // lockstep 128-thread blocks: x7 (W=3), x5 (W=5), x3 (W=9) per SM
+                if (ctx->has_ccf && width == 5) ctx->variant.coop_max = kDefaultCoopMax;
             }
         }
     }
@@ -209,7 +467,10 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
         DeviceState& d = ctx->devs[g];
         auto step = [&]() -> int {
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d.streams[b], cudaStreamNonBlocking));
+            for (int b = 0; b < kNumBuf; b++) {
+                CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d.streams[b], cudaStreamNonBlocking));
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&d.done[b], cudaEventDisableTiming));
+            }
             if (!tuned) {  // generic kernel: per-context tables in global memory
                 CUDA_TRY(ctx, generic_upload_modulus());
                 CUDA_TRY(ctx, cudaMalloc(&d.generic_tables, dense.size() * 8));
@@ -225,19 +486,26 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
         hades_destroy(ctx);
         return rc;
     }
+    init_collective(ctx);
     *out = ctx;
     return HADES_OK;
 }
 
 void hades_destroy(hades_ctx* ctx) {
     if (!ctx) return;
+    DeviceGuard guard;
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
-        for (int b = 0; b < kNumBuf; b++) {
+        for (int b = 0; b < kNumBuf; b++)
             if (d.streams[b]) cudaStreamSynchronize(d.streams[b]);
+        if (d.comm) nccl_api().CommDestroy(d.comm);
+        for (int b = 0; b < kNumBuf; b++) {
             if (d.chunk[b]) cudaFree(d.chunk[b]);
+            if (d.bounce[b]) cudaFreeHost(d.bounce[b]);
+            if (d.done[b]) cudaEventDestroy(d.done[b]);
             if (d.streams[b]) cudaStreamDestroy(d.streams[b]);
         }
+        if (d.work) cudaFree(d.work);
         if (d.generic_tables) cudaFree(d.generic_tables);
     }
     delete ctx;
@@ -246,7 +514,9 @@ void hades_destroy(hades_ctx* ctx) {
 const char* hades_last_error(const hades_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
 uint32_t hades_width(const hades_ctx* ctx) { return ctx ? ctx->width : 0; }
 int hades_device_count(const hades_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
-uint64_t hades_launch_count(const hades_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t hades_launch_count(const hades_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+const char* hades_collective(const hades_ctx* ctx) { return ctx ? ctx->collective.c_str() : ""; }
+const char* hades_last_host_path(const hades_ctx* ctx) { return ctx ? ctx->last_host_path.c_str() : ""; }
 
 int hades_perm_batch_dev(hades_ctx* ctx, int dev_index, uint64_t* d_states, size_t n, void* stream) {
     if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
@@ -260,53 +530,85 @@ int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
     if (!ctx) return fail(ctx, HADES_ERR_INVALID_ARG, "null context");
     if (n == 0) return HADES_OK;
     if (!host_states) return fail(ctx, HADES_ERR_INVALID_ARG, "null states pointer");
+    DeviceGuard guard;
     const size_t state_bytes = (size_t)ctx->width * 32;
     const size_t G = ctx->devs.size();
     size_t chunk_states = std::max<size_t>(kPermThreads, kChunkBytes / state_bytes / kPermThreads * kPermThreads);
     // Medium batches: split into kNumBuf chunks so that H2D, kernel and D2H still overlap.  Small batches
-    // (under kMinSplitBytes per chunk) go as ONE chunk: a kernel launch is one ~340 us wave regardless of its
-    // size up to ~16k states, and with pageable host memory the copies are synchronous, so splitting would
-    // only serialise several such waves.
+    // (under kMinSplitBytes per chunk) go as ONE chunk: a launch is one latency-bound wave whatever its size up to
+    // ~16k states, so splitting would only serialise several such waves.
     constexpr size_t kMinSplitBytes = (size_t)8 << 20;
-    size_t per_dev = (n + G - 1) / G;
+    const size_t per_dev = (n + G - 1) / G;
     if (per_dev < chunk_states * kNumBuf) {
         if (per_dev * state_bytes >= kMinSplitBytes * kNumBuf)
             chunk_states = std::max<size_t>(kPermThreads, (per_dev / kNumBuf + kPermThreads) / kPermThreads * kPermThreads);
         else
             chunk_states = std::max<size_t>(kPermThreads, (per_dev + kPermThreads - 1) / kPermThreads * kPermThreads);
     }
-    std::vector<size_t> lo(G), hi(G), next(G);
-    size_t max_chunks = 0;
+    // Page-locked caller memory (cudaHostAlloc, hades_host_register) is copied from directly; PAGEABLE memory of more
+    // than one chunk goes through the context's pinned staging buffers (pipeline_bounce); a small pageable batch is
+    // one synchronous staged copy either way.
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, host_states) == cudaSuccess &&
+                  (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    bool bounce = !pinned && per_dev > chunk_states;
+    if (ctx->force_bounce) bounce = true;
+    if (ctx->force_direct) bounce = false;
+    ctx->last_host_path = bounce ? "pageable: staged through pinned bounce buffers by the copy pool"
+                          : pinned ? "page-locked: direct asynchronous copies" : "pageable: single synchronous staged copy";
+    std::vector<size_t> lo(G), hi(G);
     for (size_t g = 0; g < G; g++) {
         lo[g] = n * g / G;
         hi[g] = n * (g + 1) / G;
-        next[g] = lo[g];
         if (hi[g] > lo[g]) {
             CUDA_TRY(ctx, cudaSetDevice(ctx->devs[g].ordinal));
-            int r = ensure_chunks(ctx, ctx->devs[g], std::min(chunk_states, hi[g] - lo[g]) * state_bytes);
+            const size_t bytes = std::min(chunk_states, hi[g] - lo[g]) * state_bytes;
+            int r = ensure_chunks(ctx, ctx->devs[g], bytes);
+            if (r == HADES_OK && bounce) r = ensure_bounce(ctx, ctx->devs[g], bytes);
             if (r) return r;
-            max_chunks = std::max(max_chunks, (hi[g] - lo[g] + chunk_states - 1) / chunk_states);
         }
     }
     int rc = HADES_OK;
-    for (size_t c = 0; c < max_chunks && rc == HADES_OK; c++) {
-        for (size_t g = 0; g < G && rc == HADES_OK; g++) {
-            if (next[g] >= hi[g]) continue;
-            DeviceState& d = ctx->devs[g];
-            size_t cnt = std::min(chunk_states, hi[g] - next[g]);
-            int b = (int)(c % kNumBuf);
-            uint64_t* h = host_states + next[g] * ctx->width * 4;
-            auto step = [&]() -> int {
-                CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d.chunk[b], h, cnt * state_bytes, cudaMemcpyHostToDevice, d.streams[b]));
-                int r = launch_perm_w(ctx, d.chunk[b], cnt, d.streams[b], &d);
-                if (r) return r;
-                CUDA_TRY(ctx, cudaMemcpyAsync(h, d.chunk[b], cnt * state_bytes, cudaMemcpyDeviceToHost, d.streams[b]));
-                return HADES_OK;
-            };
-            rc = step();
-            next[g] += cnt;
+    if (bounce) {  // one pipeline thread per device (each blocks on its own staging copies)
+        std::vector<int> rcs(G, HADES_OK);
+        std::vector<std::thread> th;
+        for (size_t g = 1; g < G; g++)
+            if (hi[g] > lo[g])
+                th.emplace_back([&, g] {
+                    cudaSetDevice(ctx->devs[g].ordinal);
+                    rcs[g] = pipeline_bounce(ctx, ctx->devs[g], host_states, lo[g], hi[g], chunk_states);
+                });
+        if (hi[0] > lo[0]) {
+            cudaSetDevice(ctx->devs[0].ordinal);
+            rcs[0] = pipeline_bounce(ctx, ctx->devs[0], host_states, lo[0], hi[0], chunk_states);
         }
+        for (auto& t : th) t.join();
+        for (int r : rcs) if (r != HADES_OK && rc == HADES_OK) rc = r;
+    } else {  // asynchronous copies: issue round-robin over the devices from this thread
+        size_t max_chunks = 0;
+        for (size_t g = 0; g < G; g++) max_chunks = std::max(max_chunks, (hi[g] - lo[g] + chunk_states - 1) / chunk_states);
+        for (size_t c = 0; c < max_chunks && rc == HADES_OK; c++)
+            for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+                const size_t at = lo[g] + c * chunk_states;
+                if (at >= hi[g]) continue;
+                auto step = [&]() -> int {
+                    DeviceState& d = ctx->devs[g];
+                    CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+                    // chunk c reuses buffer c % kNumBuf of its own stream: stream order protects the buffer
+                    const size_t cnt = std::min(chunk_states, hi[g] - at);
+                    const int b = (int)(c % kNumBuf);
+                    uint64_t* h = host_states + at * ctx->width * 4;
+                    CUDA_TRY(ctx, cudaMemcpyAsync(d.chunk[b], h, cnt * state_bytes, cudaMemcpyHostToDevice, d.streams[b]));
+                    if (!ctx->probe) {
+                        int r = launch_perm_w(ctx, d.chunk[b], cnt, d.streams[b], &d);
+                        if (r) return r;
+                    }
+                    CUDA_TRY(ctx, cudaMemcpyAsync(h, d.chunk[b], cnt * state_bytes, cudaMemcpyDeviceToHost, d.streams[b]));
+                    return HADES_OK;
+                };
+                rc = step();
+            }
     }
     for (size_t g = 0; g < G; g++) {
         cudaSetDevice(ctx->devs[g].ordinal);
@@ -318,6 +620,21 @@ int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
         }
     }
     return rc;
+}
+
+int hades_copy_probe(hades_ctx* ctx, uint64_t* host_states, size_t n) {
+    if (!ctx) return fail(ctx, HADES_ERR_INVALID_ARG, "null context");
+    ctx->probe = true;
+    int rc = hades_perm_batch(ctx, host_states, n);
+    ctx->probe = false;
+    return rc;
+}
+
+int hades_set_host_path(hades_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return fail(ctx, HADES_ERR_INVALID_ARG, "mode must be 0 (auto), 1 (bounce) or 2 (direct)");
+    ctx->force_bounce = mode == 1;
+    ctx->force_direct = mode == 2;
+    return HADES_OK;
 }
 
 int hades_merkle_reduce_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_nodes, size_t n_nodes, int levels,
@@ -398,26 +715,26 @@ int hades_merkle_root_ragged(hades_ctx* ctx, const uint64_t* host_leaves, size_t
         memcpy(root, host_leaves, 32);
         return HADES_OK;
     }
+    DeviceGuard guard;
     DeviceState& d = ctx->devs[0];
-    uint64_t *d_leaves = nullptr, *d_tree = nullptr;
     const size_t nodes = hades_merkle_tree_nodes(n_leaves);
-    auto step = [&]() -> int {
-        CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-        CUDA_TRY(ctx, cudaMalloc(&d_leaves, n_leaves * 32));
-        CUDA_TRY(ctx, cudaMalloc(&d_tree, nodes * 32));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_leaves, host_leaves, n_leaves * 32, cudaMemcpyHostToDevice, d.streams[0]));
-        int r = hades_merkle_tree_dev(ctx, 0, d_leaves, n_leaves, d_tree, d.streams[0]);
-        if (r) return r;
-        CUDA_TRY(ctx, cudaMemcpyAsync(root, d_tree + (nodes - 1) * 4, 32, cudaMemcpyDeviceToHost, d.streams[0]));
-        CUDA_TRY(ctx, cudaStreamSynchronize(d.streams[0]));
-        return HADES_OK;
-    };
-    int rc = step();
-    cudaFree(d_leaves);
-    cudaFree(d_tree);
-    return rc;
+    CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+    int r = ensure_work(ctx, d, (n_leaves + nodes) * 32);  // persistent scratch: leaves | interior levels
+    if (r) return r;
+    uint64_t* d_leaves = d.work;
+    uint64_t* d_tree = d.work + n_leaves * 4;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_leaves, host_leaves, n_leaves * 32, cudaMemcpyHostToDevice, d.streams[0]));
+    r = hades_merkle_tree_dev(ctx, 0, d_leaves, n_leaves, d_tree, d.streams[0]);
+    if (r) return r;
+    CUDA_TRY(ctx, cudaMemcpyAsync(root, d_tree + (nodes - 1) * 4, 32, cudaMemcpyDeviceToHost, d.streams[0]));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.streams[0]));
+    return HADES_OK;
 }
 
+// Sharded root: device g reduces leaves [g n/G, (g+1) n/G) to 1-2 subtree roots, the roots are
+// all-gathered (ncclAllGather over the context's communicator, in place: 32-64 B per device), and every device
+// finishes the top levels redundantly; the root is read back from the first device.  All devices are issued
+// before anything is waited for; buffers are the context's persistent scratch.
 int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]) {
     if (!ctx || !host_leaves || !root) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
@@ -427,38 +744,90 @@ int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leav
         memcpy(root, host_leaves, 32);
         return HADES_OK;
     }
-    // use the largest power-of-two device count that leaves >= 4 whole subtrees' worth of work each
+    DeviceGuard guard;
+    const size_t Gall = ctx->devs.size();
+    // shard over ALL devices of the context when their number is a power of two and every device gets at least 1024
+    // leaves (the communicator spans all of them); otherwise the first device does the whole tree
     size_t G = 1;
-    while (G * 2 <= ctx->devs.size() && n_leaves / (G * 2) >= 1024) G *= 2;
-    size_t per_dev = n_leaves / G;                 // = 4^a or 2*4^a
-    int sub_levels = 0;                            // levels each device can reduce on its own range
-    while (((per_dev >> (2 * (sub_levels + 1))) << (2 * (sub_levels + 1))) == per_dev && (per_dev >> (2 * (sub_levels + 1))) >= 1)
+    if (Gall > 1 && (Gall & (Gall - 1)) == 0 && n_leaves / Gall >= 1024) G = Gall;
+    const size_t per_dev = n_leaves / G;                 // = 4^a or 2*4^a
+    int sub_levels = 0;                                  // levels each device can reduce on its own range
+    while ((per_dev >> (2 * (sub_levels + 1))) >= 1 && ((per_dev >> (2 * (sub_levels + 1))) << (2 * (sub_levels + 1))) == per_dev)
         sub_levels++;
-    size_t roots_per_dev = per_dev >> (2 * sub_levels);  // 1 or 2
-    size_t n_roots = roots_per_dev * G;
-    std::vector<uint64_t> roots(n_roots * 4);
-    struct Bufs { uint64_t *leaves = nullptr, *scratch = nullptr, *out = nullptr; };
-    std::vector<Bufs> bufs(G);
+    const size_t roots_per_dev = per_dev >> (2 * sub_levels);  // 1 or 2
+    const size_t n_roots = roots_per_dev * G;
+    const int top_levels = log4_exact(n_roots);
+    if (top_levels < 0) return fail(ctx, HADES_ERR_NOT_POWER_OF_4, "internal: %zu subtree roots", n_roots);
+    // scratch layout per device (32-byte elements): leaves | ping-pong levels | gathered roots | result
+    const size_t scratch_elems = per_dev / 4 + per_dev / 16 + 8;
+    const size_t total_elems = per_dev + scratch_elems + n_roots + 8 + 1;
     int rc = HADES_OK;
-    auto cleanup = [&]() {
-        for (size_t g = 0; g < G; g++) {
-            cudaSetDevice(ctx->devs[g].ordinal);
-            cudaFree(bufs[g].leaves); cudaFree(bufs[g].scratch); cudaFree(bufs[g].out);
-        }
-    };
     for (size_t g = 0; g < G && rc == HADES_OK; g++) {
         auto step = [&]() -> int {
             DeviceState& d = ctx->devs[g];
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].leaves, per_dev * 32));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].scratch, (per_dev / 4 + per_dev / 16 + 4) * 32));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].out, std::max<size_t>(roots_per_dev, 1) * 32));
-            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].leaves, host_leaves + g * per_dev * 4, per_dev * 32,
-                                          cudaMemcpyHostToDevice, d.streams[0]));
-            int r = merkle_reduce(ctx, bufs[g].leaves, per_dev, sub_levels, bufs[g].scratch, bufs[g].out, d.streams[0]);
+            int r = ensure_work(ctx, d, total_elems * 32);
             if (r) return r;
-            CUDA_TRY(ctx, cudaMemcpyAsync(roots.data() + g * roots_per_dev * 4, bufs[g].out, roots_per_dev * 32,
-                                          cudaMemcpyDeviceToHost, d.streams[0]));
+            uint64_t* leaves = d.work;
+            uint64_t* scratch = leaves + per_dev * 4;
+            uint64_t* gathered = scratch + scratch_elems * 4;
+            CUDA_TRY(ctx, cudaMemcpyAsync(leaves, host_leaves + g * per_dev * 4, per_dev * 32, cudaMemcpyHostToDevice, d.streams[0]));
+            // own subtree roots land in their slot of the gather buffer (in-place all-gather)
+            return merkle_reduce(ctx, leaves, per_dev, sub_levels, scratch, gathered + g * roots_per_dev * 4, d.streams[0]);
+        };
+        rc = step();
+    }
+    if (rc == HADES_OK && G > 1) {
+        auto gather = [&]() -> int {
+            auto gathered_of = [&](size_t g) { return ctx->devs[g].work + (per_dev + scratch_elems) * 4; };
+            if (ctx->use_nccl) {
+                NcclApi& api = nccl_api();
+                NCCL_TRY(ctx, api.GroupStart());
+                for (size_t g = 0; g < G; g++) {
+                    uint64_t* buf = gathered_of(g);
+                    ncclResult_t r = api.AllGather(buf + g * roots_per_dev * 4, buf, roots_per_dev * 4, ncclUint64, ctx->devs[g].comm,
+                                                   ctx->devs[g].streams[0]);
+                    if (r != ncclSuccess) {
+                        api.GroupEnd();
+                        return fail(ctx, HADES_ERR_CUDA, "ncclAllGather failed: %s", api.GetErrorString(r));
+                    }
+                }
+                NCCL_TRY(ctx, api.GroupEnd());
+            } else {  // no communicator (a device listed twice, or no NCCL library): direct peer copies
+                for (size_t g = 0; g < G; g++) {
+                    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[g].ordinal));
+                    CUDA_TRY(ctx, cudaEventRecord(ctx->devs[g].done[0], ctx->devs[g].streams[0]));
+                }
+                for (size_t g = 0; g < G; g++) {
+                    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[g].ordinal));
+                    for (size_t h = 0; h < G; h++) {
+                        if (h == g) continue;
+                        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->devs[g].streams[0], ctx->devs[h].done[0], 0));
+                        CUDA_TRY(ctx, cudaMemcpyPeerAsync(gathered_of(g) + h * roots_per_dev * 4, ctx->devs[g].ordinal,
+                                                          gathered_of(h) + h * roots_per_dev * 4, ctx->devs[h].ordinal,
+                                                          roots_per_dev * 32, ctx->devs[g].streams[0]));
+                    }
+                }
+            }
+            return HADES_OK;
+        };
+        rc = gather();
+    }
+    // top levels on every device (redundantly); result read from the first
+    for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+        auto step = [&]() -> int {
+            DeviceState& d = ctx->devs[g];
+            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+            uint64_t* scratch = d.work + per_dev * 4;
+            uint64_t* gathered = scratch + scratch_elems * 4;
+            uint64_t* result = gathered + (n_roots + 8) * 4;
+            if (top_levels == 0) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(result, gathered, 32, cudaMemcpyDeviceToDevice, d.streams[0]));
+            } else {
+                int r = merkle_reduce(ctx, gathered, n_roots, top_levels, scratch, result, d.streams[0]);
+                if (r) return r;
+            }
+            if (g == 0) CUDA_TRY(ctx, cudaMemcpyAsync(root, result, 32, cudaMemcpyDeviceToHost, d.streams[0]));
             return HADES_OK;
         };
         rc = step();
@@ -466,32 +835,32 @@ int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leav
     for (size_t g = 0; g < G; g++) {
         cudaSetDevice(ctx->devs[g].ordinal);
         cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[0]);
-        if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "merkle subtree pass failed: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "merkle pass failed on device %d: %s", ctx->devs[g].ordinal, cudaGetErrorString(e));
     }
-    if (rc == HADES_OK && n_roots > 1) {
-        // top of the tree on the first device (n_roots <= 2*G nodes)
-        auto step = [&]() -> int {
-            DeviceState& d = ctx->devs[0];
-            int top_levels = log4_exact(n_roots);
-            if (top_levels < 0) return fail(ctx, HADES_ERR_NOT_POWER_OF_4, "internal: %zu subtree roots", n_roots);
-            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[0].leaves, roots.data(), n_roots * 32, cudaMemcpyHostToDevice, d.streams[0]));
-            int r = merkle_reduce(ctx, bufs[0].leaves, n_roots, top_levels, bufs[0].scratch, bufs[0].out, d.streams[0]);
-            if (r) return r;
-            CUDA_TRY(ctx, cudaMemcpyAsync(roots.data(), bufs[0].out, 32, cudaMemcpyDeviceToHost, d.streams[0]));
-            CUDA_TRY(ctx, cudaStreamSynchronize(d.streams[0]));
-            return HADES_OK;
-        };
-        rc = step();
-    }
-    cleanup();
-    if (rc == HADES_OK) memcpy(root, roots.data(), 32);
     return rc;
 }
 
-int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
-                           size_t n_msgs, uint64_t* d_out, void* stream) {
+// capacity word of the sponge: zero, or the caller's domain tag (a canonical field element, Montgomery limbs)
+static int make_tag(hades_ctx* ctx, const uint64_t* tag, SpongeTag& out) {
+    memset(&out, 0, sizeof out);
+    if (!tag) return HADES_OK;
+    static const uint64_t kP[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+    bool below = false;
+    for (int i = 3; i >= 0 && !below; i--) {
+        if (tag[i] < kP[i]) below = true;
+        else if (tag[i] > kP[i]) break;
+    }
+    if (!below) return fail(ctx, HADES_ERR_INVALID_ARG, "the domain tag must be a canonical field element (< p)");
+    for (int k = 0; k < 8; k++) out.l[k] = (uint32_t)(tag[k / 2] >> (32 * (k & 1)));
+    return HADES_OK;
+}
+
+static int sponge_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
+                      size_t n_msgs, uint64_t* d_out, const uint64_t* tag, void* stream) {
     if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    SpongeTag stag;
+    if (int r = make_tag(ctx, tag, stag)) return r;
+    DeviceGuard guard;
     if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "sponge needs a width-5 context");
     if (n_msgs == 0) return HADES_OK;
     if (!d_offsets || !d_out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
@@ -520,11 +889,22 @@ int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elem
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(bufs.p[4], tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
     ctx->launches++;
-    CUDA_TRY(ctx, ctx->ops()->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, st));
+    CUDA_TRY(ctx, ctx->ops()->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, stag, st));
     return HADES_OK;
 }
 
-int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs, uint64_t* out) {
+int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
+                           size_t n_msgs, uint64_t* d_out, void* stream) {
+    return sponge_dev(ctx, dev_index, d_elems, d_offsets, n_msgs, d_out, nullptr, stream);
+}
+int hades_sponge_batch_ds_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
+                              size_t n_msgs, const uint64_t domain_tag[4], uint64_t* d_out, void* stream) {
+    if (!domain_tag) return fail(ctx, HADES_ERR_INVALID_ARG, "null domain tag");
+    return sponge_dev(ctx, dev_index, d_elems, d_offsets, n_msgs, d_out, domain_tag, stream);
+}
+
+static int sponge_host(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs, uint64_t* out,
+                       const uint64_t* tag) {
     if (!ctx) return fail(ctx, HADES_ERR_INVALID_ARG, "null context");
     if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "sponge needs a width-5 context");
     if (n_msgs == 0) return HADES_OK;
@@ -546,25 +926,28 @@ int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* of
             while (g < G && acc >= total * g / G) bound[g++] = m + 1;
         }
     }
-    struct Bufs { uint64_t *elems = nullptr, *offsets = nullptr, *out = nullptr; };
-    std::vector<Bufs> bufs(G);
     int rc = HADES_OK;
-    for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+    DeviceGuard guard;
+    for (size_t g = 0; g < G && rc == HADES_OK; g++) {  // every device is issued before any is waited for
         auto step = [&]() -> int {
             DeviceState& d = ctx->devs[g];
             const size_t m0 = bound[g], cnt = bound[g + 1] - bound[g];
             if (!cnt) return HADES_OK;
             const uint64_t e0 = offsets[m0], ne = offsets[m0 + cnt] - e0;
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].elems, std::max<uint64_t>(ne, 1) * 32));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].offsets, (cnt + 1) * 8));
-            CUDA_TRY(ctx, cudaMalloc(&bufs[g].out, cnt * 32));
-            if (ne) CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].elems, elems + e0 * 4, ne * 32, cudaMemcpyHostToDevice, d.streams[0]));
-            CUDA_TRY(ctx, cudaMemcpyAsync(bufs[g].offsets, offsets + m0, (cnt + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
-            // offsets stay absolute: bias the element base pointer by the range's first offset
-            int r = hades_sponge_batch_dev(ctx, (int)g, bufs[g].elems - e0 * 4, bufs[g].offsets, cnt, bufs[g].out, d.streams[0]);
+            // persistent scratch: elements | digests | offsets
+            const size_t elems_u64 = std::max<uint64_t>(ne, 1) * 4, out_u64 = cnt * 4;
+            int r = ensure_work(ctx, d, (elems_u64 + out_u64 + cnt + 1) * 8);
             if (r) return r;
-            CUDA_TRY(ctx, cudaMemcpyAsync(out + m0 * 4, bufs[g].out, cnt * 32, cudaMemcpyDeviceToHost, d.streams[0]));
+            uint64_t* d_elems = d.work;
+            uint64_t* d_out = d_elems + elems_u64;
+            uint64_t* d_offsets = d_out + out_u64;
+            if (ne) CUDA_TRY(ctx, cudaMemcpyAsync(d_elems, elems + e0 * 4, ne * 32, cudaMemcpyHostToDevice, d.streams[0]));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_offsets, offsets + m0, (cnt + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
+            // offsets stay absolute: bias the element base pointer by the range's first offset
+            r = sponge_dev(ctx, (int)g, d_elems - e0 * 4, d_offsets, cnt, d_out, tag, d.streams[0]);
+            if (r) return r;
+            CUDA_TRY(ctx, cudaMemcpyAsync(out + m0 * 4, d_out, cnt * 32, cudaMemcpyDeviceToHost, d.streams[0]));
             return HADES_OK;
         };
         rc = step();
@@ -573,9 +956,17 @@ int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* of
         cudaSetDevice(ctx->devs[g].ordinal);
         cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[0]);
         if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "sponge pass failed: %s", cudaGetErrorString(e));
-        cudaFree(bufs[g].elems); cudaFree(bufs[g].offsets); cudaFree(bufs[g].out);
     }
     return rc;
+}
+
+int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs, uint64_t* out) {
+    return sponge_host(ctx, elems, offsets, n_msgs, out, nullptr);
+}
+int hades_sponge_batch_ds(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs,
+                          const uint64_t domain_tag[4], uint64_t* out) {
+    if (!domain_tag) return fail(ctx, HADES_ERR_INVALID_ARG, "null domain tag");
+    return sponge_host(ctx, elems, offsets, n_msgs, out, domain_tag);
 }
 
 int hades_host_register(hades_ctx* ctx, void* ptr, size_t bytes) {
@@ -679,6 +1070,12 @@ int hades_set_variant(hades_ctx* ctx, int algo, int regs) {
     if (!ctx || algo < 0 || algo > 2 || regs < 0 || regs > 10) return fail(ctx, HADES_ERR_INVALID_ARG, "variant out of range");
     if (ctx->generic()) return fail(ctx, HADES_ERR_INVALID_ARG, "width %u runs the generic kernel, which has no variants", ctx->width);
     if (algo == 2 && !ctx->has_ccf) return fail(ctx, HADES_ERR_CONSTANTS, "the canonical-form schedule could not be derived for these constants");
+    if (algo == 1 && !ctx->has_sparse) return fail(ctx, HADES_ERR_CONSTANTS, "the sparse schedule could not be derived for these constants");
+    Variant probe = ctx->variant;
+    probe.algo = algo;
+    probe.regs = regs;
+    if (!ctx->ops2[algo]->supports(probe))
+        return fail(ctx, HADES_ERR_INVALID_ARG, "launch shape regs=%d is not built for width %u, algo %d (include/hades_cuda.h)", regs, ctx->width, algo);
     ctx->variant.algo = algo;
     ctx->variant.regs = regs;
     return HADES_OK;

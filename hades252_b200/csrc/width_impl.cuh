@@ -259,7 +259,7 @@ merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ o
 template <int ALGO, int MINB>
 __global__ void __launch_bounds__(kPermThreads, MINB)
 sponge_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offsets,
-              const uint32_t* __restrict__ order, uint4* __restrict__ out, size_t n_threads) {
+              const uint32_t* __restrict__ order, uint4* __restrict__ out, size_t n_threads, const SpongeTag tag) {
     size_t t = (size_t)blockIdx.x * kPermThreads + threadIdx.x;
     if (t >= n_threads) return;
     size_t m = order ? order[t] : t;
@@ -267,6 +267,8 @@ sponge_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offs
     Fr s[5];
 #pragma unroll
     for (int j = 0; j < 5; j++) fr_set_zero(s[j]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[0].l[k] = tag.l[k];  // capacity word: zero or the domain tag
     bool padded = false;
 #pragma unroll 1
     while (!padded) {
@@ -296,7 +298,7 @@ sponge_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offs
 // permuting a dead state and has already captured its digest.
 __global__ void __launch_bounds__(kPermThreads, 4)
 sponge_lockstep_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offsets,
-                       const uint32_t* __restrict__ order, uint4* __restrict__ out, size_t n_threads) {
+                       const uint32_t* __restrict__ order, uint4* __restrict__ out, size_t n_threads, const SpongeTag tag) {
     __shared__ unsigned int s_max_blocks;
     if (threadIdx.x == 0) s_max_blocks = 0;
     __syncthreads();
@@ -311,6 +313,8 @@ sponge_lockstep_kernel(const uint4* __restrict__ elems, const uint64_t* __restri
     Fr s[5], digest;
 #pragma unroll
     for (int j = 0; j < 5; j++) fr_set_zero(s[j]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[0].l[k] = tag.l[k];  // capacity word: zero or the domain tag
     fr_set_zero(digest);
     bool padded = false;
 #pragma unroll 1
@@ -493,14 +497,14 @@ cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out
     return cudaGetLastError();
 }
 cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
-                          uint64_t* d_out, size_t n_threads, cudaStream_t s) {
+                          uint64_t* d_out, size_t n_threads, SpongeTag tag, cudaStream_t s) {
     if (n_threads == 0) return cudaSuccess;
     // lockstep shapes do not apply (messages differ in length); the optimised kernel fits 96 registers, so
     // use 5 blocks/SM (measured: 225 ms vs 249 ms at 4 blocks/SM for the 2^22-message config)
 #if HADES_ALGO >= 1
     if (v.regs >= 4 && d_order != nullptr) {  // lockstep launch shapes: sorted messages, block-uniform trip counts
         sponge_lockstep_kernel<<<(unsigned)((n_threads + kPermThreads - 1) / kPermThreads), kPermThreads, 0, s>>>(
-            reinterpret_cast<const uint4*>(d_elems), d_offsets, d_order, reinterpret_cast<uint4*>(d_out), n_threads);
+            reinterpret_cast<const uint4*>(d_elems), d_offsets, d_order, reinterpret_cast<uint4*>(d_out), n_threads, tag);
         return cudaGetLastError();
     }
 #endif
@@ -509,7 +513,7 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     HADES_DISPATCH(sponge_kernel, v,
                    <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_elems), d_offsets, d_order,
-                                                             reinterpret_cast<uint4*>(d_out), n_threads));
+                                                             reinterpret_cast<uint4*>(d_out), n_threads, tag));
     return cudaGetLastError();
 }
 #endif
@@ -541,6 +545,7 @@ cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* o
     if (!strcmp(kernel, "perm") && v.regs == 7) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<384, 1>);
     if (!strcmp(kernel, "perm") && v.regs == 8) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<640, 1>);
     if (!strcmp(kernel, "perm") && v.regs == 9) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 4>);
+    if (!strcmp(kernel, "perm") && v.regs == 10) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<128, 6>);
 #endif
 #if HADES_W == 5
     if (!strcmp(kernel, "merkle") && v.regs >= 4) return cudaFuncGetAttributes(out, merkle_level_lockstep_kernel<128, 5>);
@@ -555,13 +560,22 @@ cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* o
     return cudaErrorInvalidValue;
 }
 
+// launch shapes built for this width / schedule (must mirror the switch in launch_perm)
+bool supports(Variant v) {
+    if (v.regs < 0) return false;
+    if (v.regs <= 3) return true;
+    if (kAlgo == 0) return false;  // the dense schedule has no lockstep build
+    if (v.regs <= 5) return true;
+    return v.regs <= (W == 5 ? 10 : 7);
+}
+
 const WidthOps kOps = {W, kAlgo, (size_t)kTableEntries * 4, upload, launch_perm,
 #if HADES_W == 5
                        launch_merkle_level, launch_sponge,
 #else
                        nullptr, nullptr,
 #endif
-                       func_attributes};
+                       func_attributes, supports};
 
 }  // namespace
 }  // namespace hades

@@ -26,6 +26,11 @@ struct Variant {
 };
 constexpr int kPermThreads = 128;
 
+// initial capacity word (word 0) of the sponge state: zero, or a domain tag (8 x u32 Montgomery limbs)
+struct SpongeTag {
+    uint32_t l[8];
+};
+
 struct WidthOps {
     int width;
     int algo;          // 0: dense table (67*W + W*W entries); 1: OptLayout<W>::kEntries; 2: CcfLayout<W>::kEntries
@@ -36,8 +41,9 @@ struct WidthOps {
     // n_out == ceil(n_in / 4); the last node of a ragged level hashes its present children under the matching bitmask
     cudaError_t (*launch_merkle_level)(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, size_t n_in, cudaStream_t s);
     cudaError_t (*launch_sponge)(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
-                                 uint64_t* d_out, size_t n_threads, cudaStream_t s);
+                                 uint64_t* d_out, size_t n_threads, SpongeTag tag, cudaStream_t s);
     cudaError_t (*func_attributes)(const char* kernel, Variant v, cudaFuncAttributes* out);
+    bool (*supports)(Variant v);  // is this launch shape (regs) built for this width / schedule?
 };
 
 // one translation unit per (width, algo): hades_w{3,5,9}.cu (sparse), _dense.cu, _ccf.cu

@@ -157,17 +157,32 @@ class CudaStrategy(Strategy):
         self._check(self._lib.hades_merkle_open_dev(self._ctx, dev_index, leaves_ptr, tree_ptr, n_leaves, index_ptr, n_open,
                                                     branch_ptr, stream))
 
-    def sponge_batch(self, elems: np.ndarray, offsets: np.ndarray) -> np.ndarray:
-        """Sponge digests of n messages in CSR form; elems uint64 [total, 4], offsets uint64 [n+1]."""
+    def sponge_batch(self, elems: np.ndarray, offsets: np.ndarray, domain_tag: Optional[np.ndarray] = None) -> np.ndarray:
+        """Sponge digests of n messages in CSR form; elems uint64 [total, 4], offsets uint64 [n+1].
+        `domain_tag` (uint64 [4], one canonical field element): initial capacity word (domain separation)."""
         _as_u64(offsets, "offsets")
         if offsets.ndim != 1 or offsets.shape[0] < 1:
             raise ValueError("offsets must be a 1-d array of n+1 entries")
         n = offsets.shape[0] - 1
         if elems.size:
             _as_u64(elems, "elems")
+            if elems.ndim != 2 or elems.shape[1] != 4:
+                raise ValueError("elems must have shape [total, 4]")
+        # the C side copies elems[offsets[0] .. offsets[n]): a CSR that points past the array would read out of bounds
+        if int(offsets[0]) != 0:
+            raise ValueError("offsets[0] must be 0")
+        if int(offsets[-1]) > (elems.shape[0] if elems.size else 0):
+            raise ValueError(f"offsets[-1]={int(offsets[-1])} exceeds the {elems.shape[0] if elems.size else 0} elements given")
         out = np.empty((n, 4), dtype=np.uint64)
-        self._check(self._lib.hades_sponge_batch(self._ctx, elems.ctypes.data if elems.size else None,
-                                                 offsets.ctypes.data, n, out.ctypes.data))
+        ep = elems.ctypes.data if elems.size else None
+        if domain_tag is None:
+            self._check(self._lib.hades_sponge_batch(self._ctx, ep, offsets.ctypes.data, n, out.ctypes.data))
+        else:
+            tag = np.ascontiguousarray(domain_tag, dtype=np.uint64)
+            if tag.shape != (4,):
+                raise ValueError("domain_tag must be one field element: uint64 [4]")
+            self._check(self._lib.hades_sponge_batch_ds(self._ctx, ep, offsets.ctypes.data, n,
+                                                        tag.ctypes.data_as(_native.u64p), out.ctypes.data))
         return out
 
     def sponge_batch_device(self, elems_ptr: int, offsets_ptr: int, n_msgs: int, out_ptr: int, stream: int = 0,
@@ -204,6 +219,22 @@ class CudaStrategy(Strategy):
         """Batches / Merkle levels of at most `max_states` states use the cooperative 8-lanes-per-state kernels
         (width 5, algo 2; 0 disables; bit-identical results)."""
         self._check(self._lib.hades_set_coop_threshold(self._ctx, max_states))
+
+    def copy_probe_ptr(self, host_ptr: int, n: int) -> None:
+        """perm_batch's host pipeline without the kernel (bare H2D + D2H ceiling)."""
+        self._check(self._lib.hades_copy_probe(self._ctx, host_ptr, n))
+
+    def set_host_path(self, mode: int) -> None:
+        """0 automatic, 1 always pinned bounce buffers, 2 always direct copies"""
+        self._check(self._lib.hades_set_host_path(self._ctx, mode))
+
+    @property
+    def last_host_path(self) -> str:
+        return self._lib.hades_last_host_path(self._ctx).decode()
+
+    @property
+    def collective(self) -> str:
+        return self._lib.hades_collective(self._ctx).decode()
 
     def host_register(self, ptr: int, nbytes: int) -> None:
         self._check(self._lib.hades_host_register(self._ctx, ptr, nbytes))

@@ -14,6 +14,7 @@
  *
  * All functions return 0 on success or a non-zero hades_status; hades_last_error() gives the
  * message.  There is no CPU fallback: without a usable CUDA device hades_init fails.
+ * Every entry point restores the calling thread's current CUDA device before it returns.
  *
  * Threading: one hades_ctx is single-caller (mirrors `&mut self`); distinct contexts may be used
  * concurrently.  The constant tables live in per-device `__constant__` memory and are therefore
@@ -88,8 +89,10 @@ int hades_perm_batch_dev(hades_ctx* ctx, int dev_index, uint64_t* d_states, size
 /*
  * 4-ary Merkle root: node = perm([15, c0, c1, c2, c3])[1] (bitmask of present children in word 0,
  * output word 1); leaves are field elements used as level-0 nodes; n_leaves = 4^k.  Width-5 contexts
- * only.  HOST pointers; leaf ranges are sharded over the context's devices, subtree roots are
- * gathered and the top levels finished on the first device.  (Build-defined composition: the
+ * only.  HOST pointers.  With a power-of-two number of devices (and at least 1024 leaves each) the leaf
+ * ranges are sharded over the context's devices: every device reduces its range to 1-2 subtree roots, the
+ * roots are all-gathered with ncclAllGather (communicator created by hades_init with ncclCommInitAll;
+ * see hades_collective) and every device finishes the top levels.  (Build-defined composition: the
  * reference removed its Merkle code in 0.7.0, CHANGELOG.md:159-162.)
  */
 int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]);
@@ -138,11 +141,37 @@ int hades_sponge_batch(hades_ctx* ctx, const uint64_t* elems, const uint64_t* of
 int hades_sponge_batch_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
                            size_t n_msgs, uint64_t* d_out, void* stream);
 
-/* Page-lock / unlock a caller-owned host range so hades_perm_batch copies run asynchronously. */
+/*
+ * Sponge with domain separation: as hades_sponge_batch, but the capacity word (word 0) starts as
+ * `domain_tag` (one canonical field element, Montgomery limbs) instead of zero, so that different tags give
+ * independent hash functions over the same permutation (the convention of the callers of `perm`: the capacity
+ * element carries the domain / length tag, the rate words the message).  A zero tag equals hades_sponge_batch.
+ */
+int hades_sponge_batch_ds(hades_ctx* ctx, const uint64_t* elems, const uint64_t* offsets, size_t n_msgs,
+                          const uint64_t domain_tag[4], uint64_t* out);
+int hades_sponge_batch_ds_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, const uint64_t* d_offsets,
+                              size_t n_msgs, const uint64_t domain_tag[4], uint64_t* d_out, void* stream);
+
+/* The collective multi-device contexts gather subtree roots with: "ncclAllGather (NCCL x.y.z, ...)", or
+ * "peer copies (...reason...)" when no communicator could be created, or "none (single device)". */
+const char* hades_collective(const hades_ctx* ctx);
+
+/* Page-lock / unlock a caller-owned host range so hades_perm_batch copies run asynchronously.  Not required:
+ * PAGEABLE buffers larger than one chunk are staged through the context's own pinned buffers by a pool of
+ * host threads (HADES_COPY_THREADS, default min(16, cores)). */
 int hades_host_register(hades_ctx* ctx, void* ptr, size_t bytes);
 int hades_host_unregister(hades_ctx* ctx, void* ptr);
 
 /* ---- measurement helpers (bench / tests); not part of the reference-facing surface ---------- */
+
+/* hades_perm_batch's host pipeline WITHOUT the kernel (same chunking, same buffers, same streams): the bare
+ * H2D + D2H copy ceiling of the box, for bench.py's e2e analysis.  The buffer comes back unchanged. */
+int hades_copy_probe(hades_ctx* ctx, uint64_t* host_states, size_t n);
+/* Force the host path of hades_perm_batch: 0 = automatic (page-locked memory: direct asynchronous copies;
+ * pageable: pinned bounce buffers), 1 = always bounce, 2 = always direct.  For A/B measurements. */
+int hades_set_host_path(hades_ctx* ctx, int mode);
+/* Which host path the last hades_perm_batch / hades_copy_probe took (static string). */
+const char* hades_last_host_path(const hades_ctx* ctx);
 
 /* Fill d_out with n_elems synthetic field elements: element e (global index first_elem + i), limb l
  * = splitmix64(seed + 4*e + l), top limb masked to 62 bits (< 2^254 < p).  SURVEY.md 8(d). */
@@ -167,7 +196,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
  * could not be derived for the context's constants); launch shape `regs`: 0/1/2/3 = 128-thread blocks
  * with at most 128/168/255/96 registers per thread, 4/5 = lockstep blocks of 256/512 threads, 6.. = lockstep
  * 128-thread blocks (the default; see hades252_b200/csrc/width_ops.hpp). */
-int hades_set_variant(hades_ctx* ctx, int algo, int regs);
+int hades_set_variant(hades_ctx* ctx, int algo, int regs);  /* HADES_ERR_INVALID_ARG for a shape not built for the width */
 /* Small-batch path: batches (and Merkle levels) of at most `max_states` states run the cooperative kernels --
  * one state per group of 8 lanes, 2.1x lower latency (125 us) than the one-thread-per-state kernel, which is
  * latency-bound below ~2^14 states (a lone `Strategy::perm`, strategies.rs:140, is a batch of one).  Width 5,

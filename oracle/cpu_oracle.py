@@ -43,6 +43,8 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_merkle_tree.restype = ctypes.c_int
         _lib.oracle_sponge_batch.argtypes = [_u64p, _u64p, ctypes.c_size_t, _u64p, _u64p, _u64p, ctypes.c_int]
         _lib.oracle_sponge_batch.restype = ctypes.c_int
+        _lib.oracle_sponge_batch_ds.argtypes = [_u64p, _u64p, ctypes.c_size_t, _u64p, _u64p, _u64p, _u64p, ctypes.c_int]
+        _lib.oracle_sponge_batch_ds.restype = ctypes.c_int
         _lib.oracle_load_table.argtypes = [_u8p, ctypes.c_size_t, _u64p]
         _lib.oracle_load_table.restype = None
         _lib.oracle_gen_elems.argtypes = [_u64p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_uint64]
@@ -108,7 +110,9 @@ def merkle_root(leaves: np.ndarray, nthreads: int | None = None) -> np.ndarray:
     return root
 
 
-def sponge_batch(elems: np.ndarray, offsets: np.ndarray, nthreads: int | None = None) -> np.ndarray:
+def sponge_batch(elems: np.ndarray, offsets: np.ndarray, nthreads: int | None = None,
+                 domain_tag: np.ndarray | None = None) -> np.ndarray:
+    """domain_tag: uint64 [4] Montgomery limbs of the capacity word (None = zero, the plain sponge)"""
     elems = np.ascontiguousarray(elems, dtype=np.uint64).reshape(-1, 4)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     n = offsets.shape[0] - 1
@@ -116,8 +120,12 @@ def sponge_batch(elems: np.ndarray, offsets: np.ndarray, nthreads: int | None = 
     out = np.empty((n, 4), dtype=np.uint64)
     if elems.shape[0] == 0:
         elems = np.zeros((1, 4), dtype=np.uint64)
-    lib().oracle_sponge_batch(_p(elems), _p(offsets), n, _p(ark), _p(mds), _p(out),
-                              nthreads or host_threads())
+    if domain_tag is None:
+        lib().oracle_sponge_batch(_p(elems), _p(offsets), n, _p(ark), _p(mds), _p(out), nthreads or host_threads())
+    else:
+        tag = np.ascontiguousarray(domain_tag, dtype=np.uint64)
+        lib().oracle_sponge_batch_ds(_p(elems), _p(offsets), n, _p(tag), _p(ark), _p(mds), _p(out),
+                                     nthreads or host_threads())
     return out
 
 

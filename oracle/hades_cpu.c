@@ -265,11 +265,12 @@ int oracle_merkle_tree(const uint64_t *leaves, size_t n_leaves, const uint64_t *
 }
 
 /* ------------------------------------------------------------------------- sponge */
-typedef struct { const fr_t *elems; const uint64_t *off; fr_t *out; const fr_t *ark, *mds; fr_t one; } sponge_ctx;
+typedef struct { const fr_t *elems; const uint64_t *off; fr_t *out; const fr_t *ark, *mds; fr_t one; fr_t tag; } sponge_ctx;
 static void sponge_range(void *p, size_t lo, size_t hi) {
     sponge_ctx *c = p;
     for (size_t m = lo; m < hi; m++) {
         fr_t s[5]; memset(s, 0, sizeof s);
+        s[0] = c->tag;  /* capacity word: zero, or the domain tag (oracle_sponge_batch_ds) */
         size_t b = c->off[m], e = c->off[m + 1];
         int done = 0;
         while (!done) {
@@ -286,9 +287,20 @@ static void sponge_range(void *p, size_t lo, size_t hi) {
 /* rate 4 / capacity 1, pad = single 1 then zeros; digest = word 1.  CSR offsets (n+1). */
 int oracle_sponge_batch(const uint64_t *elems, const uint64_t *offsets, size_t n_msgs,
                         const uint64_t *ark, const uint64_t *mds, uint64_t *out, int nthreads) {
-    sponge_ctx c = {(const fr_t *)elems, offsets, (fr_t *)out, (const fr_t *)ark, (const fr_t *)mds, {{0}}};
+    sponge_ctx c = {(const fr_t *)elems, offsets, (fr_t *)out, (const fr_t *)ark, (const fr_t *)mds, {{0}}, {{0}}};
     uint64_t raw1[4] = {1, 0, 0, 0};
     oracle_from_raw(raw1, c.one.l);
+    parallel_for(n_msgs, nthreads, sponge_range, &c);
+    return 0;
+}
+/* same with domain separation: the capacity word (word 0) starts as `tag` (Montgomery limbs, < p) instead of zero
+ * (hades_ref.py sponge(message, domain)).  Build-defined like the sponge itself: the reference holds no sponge. */
+int oracle_sponge_batch_ds(const uint64_t *elems, const uint64_t *offsets, size_t n_msgs, const uint64_t *tag,
+                           const uint64_t *ark, const uint64_t *mds, uint64_t *out, int nthreads) {
+    sponge_ctx c = {(const fr_t *)elems, offsets, (fr_t *)out, (const fr_t *)ark, (const fr_t *)mds, {{0}}, {{0}}};
+    uint64_t raw1[4] = {1, 0, 0, 0};
+    oracle_from_raw(raw1, c.one.l);
+    memcpy(c.tag.l, tag, 32);
     parallel_for(n_msgs, nthreads, sponge_range, &c);
     return 0;
 }

@@ -256,13 +256,16 @@ def merkle_verify(leaf: int, index: int, n_leaves: int, branch: Sequence[Sequenc
     return m == 1 and node == root
 
 
-def sponge(message: Iterable[int]) -> int:
-    """rate 4 / capacity 1: state [0;5]; pad with one 1 then zeros to a multiple of 4;
-    per block add the 4 elements into words 1..4 and perm; output word 1."""
+def sponge(message: Iterable[int], domain: int = 0) -> int:
+    """rate 4 / capacity 1: state [domain, 0, 0, 0, 0]; pad with one 1 then zeros to a multiple of 4;
+    per block add the 4 elements into words 1..4 and perm; output word 1.
+    `domain` (default 0) is the domain-separation tag carried by the capacity word: different tags give independent
+    hash functions over the same permutation (the convention of the out-of-tree callers of `perm`, SURVEY.md 8(f)4:
+    capacity element = domain / length tag, rate words = message).  Build-defined like the sponge itself."""
     msg = [m % P for m in message] + [1]
     while len(msg) % 4:
         msg.append(0)
-    state = [0] * WIDTH
+    state = [domain % P] + [0] * (WIDTH - 1)
     for b in range(0, len(msg), 4):
         for k in range(4):
             state[1 + k] = (state[1 + k] + msg[b + k]) % P

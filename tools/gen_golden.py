@@ -54,9 +54,14 @@ def main():
     msgs = [[], [1], [1, 2, 3], [1, 2, 3, 4], [1, 2, 3, 4, 5], list(range(1, 10)), [P - 1] * 8, [0] * 4]
     sponge = [{"message": [hex(x) for x in m], "digest": hex(H.sponge(m)), "digest_mont_limbs": limbs_hex(H.sponge(m))}
               for m in msgs]
+    # sponge with domain separation: capacity word = tag (hades_ref.sponge(message, domain))
+    tags = [1, 0xF, 1 << 32, (1 << 64) + 3, P - 1]
+    sponge_ds = [{"message": [hex(x) for x in m], "domain": hex(t), "domain_mont_limbs": limbs_hex(t),
+                  "digest": hex(H.sponge(m, t)), "digest_mont_limbs": limbs_hex(H.sponge(m, t))}
+                 for t in tags for m in ([], [1, 2, 3, 4], list(range(1, 10)))]
     out = {"generator": "tools/gen_golden.py (oracle/hades_ref.py)", "modulus": hex(P),
            "ark_bin_sha256": H.ARK_BIN_SHA256, "mds_bin_sha256": H.MDS_BIN_SHA256,
-           "perm": perm_cases, "merkle": merkle, "sponge": sponge}
+           "perm": perm_cases, "merkle": merkle, "sponge": sponge, "sponge_ds": sponge_ds}
     path = os.path.join(ROOT, "tests", "golden", "hades252_kat.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
