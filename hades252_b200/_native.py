@@ -23,6 +23,7 @@ SIGNATURES = {
     "hades_perm_batch": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_size_t]),
     "hades_perm_batch_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "hades_merkle_root": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_size_t, u64p]),
+    "hades_merkle_root_sharded_dev": (ctypes.c_int, [ctx_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, u64p]),
     "hades_merkle_reduce_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "hades_merkle_tree_nodes": (ctypes.c_size_t, [ctypes.c_size_t]),

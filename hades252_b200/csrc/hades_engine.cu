@@ -735,21 +735,18 @@ int hades_merkle_root_ragged(hades_ctx* ctx, const uint64_t* host_leaves, size_t
 // all-gathered (ncclAllGather over the context's communicator, in place: 32-64 B per device), and every device
 // finishes the top levels redundantly; the root is read back from the first device.  All devices are issued
 // before anything is waited for; buffers are the context's persistent scratch.
-int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]) {
-    if (!ctx || !host_leaves || !root) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
-    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+// host_leaves != nullptr: leaves are uploaded from the host; else d_leaves[g] = device g's resident leaf range.
+static int merkle_root_sharded(hades_ctx* ctx, const uint64_t* host_leaves, const uint64_t* const* d_leaves, size_t n_leaves,
+                               uint64_t root[4]) {
     int depth = log4_exact(n_leaves);
     if (depth < 0) return fail(ctx, HADES_ERR_NOT_POWER_OF_4, "number of leaves (%zu) must be a power of 4", n_leaves);
-    if (depth == 0) {
-        memcpy(root, host_leaves, 32);
-        return HADES_OK;
-    }
     DeviceGuard guard;
     const size_t Gall = ctx->devs.size();
     // shard over ALL devices of the context when their number is a power of two and every device gets at least 1024
     // leaves (the communicator spans all of them); otherwise the first device does the whole tree
     size_t G = 1;
     if (Gall > 1 && (Gall & (Gall - 1)) == 0 && n_leaves / Gall >= 1024) G = Gall;
+    if (!host_leaves && G != Gall) return fail(ctx, HADES_ERR_INVALID_ARG, "resident leaves need a power-of-two number of devices and >= 1024 leaves each");
     const size_t per_dev = n_leaves / G;                 // = 4^a or 2*4^a
     int sub_levels = 0;                                  // levels each device can reduce on its own range
     while ((per_dev >> (2 * (sub_levels + 1))) >= 1 && ((per_dev >> (2 * (sub_levels + 1))) << (2 * (sub_levels + 1))) == per_dev)
@@ -758,9 +755,10 @@ int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leav
     const size_t n_roots = roots_per_dev * G;
     const int top_levels = log4_exact(n_roots);
     if (top_levels < 0) return fail(ctx, HADES_ERR_NOT_POWER_OF_4, "internal: %zu subtree roots", n_roots);
-    // scratch layout per device (32-byte elements): leaves | ping-pong levels | gathered roots | result
+    // scratch layout per device (32-byte elements): [leaves] | ping-pong levels | gathered roots | result
+    const size_t leaf_elems = host_leaves ? per_dev : 0;
     const size_t scratch_elems = per_dev / 4 + per_dev / 16 + 8;
-    const size_t total_elems = per_dev + scratch_elems + n_roots + 8 + 1;
+    const size_t total_elems = leaf_elems + scratch_elems + n_roots + 8 + 1;
     int rc = HADES_OK;
     for (size_t g = 0; g < G && rc == HADES_OK; g++) {
         auto step = [&]() -> int {
@@ -768,18 +766,25 @@ int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leav
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
             int r = ensure_work(ctx, d, total_elems * 32);
             if (r) return r;
-            uint64_t* leaves = d.work;
-            uint64_t* scratch = leaves + per_dev * 4;
+            uint64_t* scratch = d.work + leaf_elems * 4;
             uint64_t* gathered = scratch + scratch_elems * 4;
-            CUDA_TRY(ctx, cudaMemcpyAsync(leaves, host_leaves + g * per_dev * 4, per_dev * 32, cudaMemcpyHostToDevice, d.streams[0]));
+            const uint64_t* leaves = d.work;
+            if (host_leaves)
+                CUDA_TRY(ctx, cudaMemcpyAsync(d.work, host_leaves + g * per_dev * 4, per_dev * 32, cudaMemcpyHostToDevice, d.streams[0]));
+            else
+                leaves = d_leaves[g];
             // own subtree roots land in their slot of the gather buffer (in-place all-gather)
+            if (sub_levels == 0) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(gathered + g * roots_per_dev * 4, leaves, roots_per_dev * 32, cudaMemcpyDeviceToDevice, d.streams[0]));
+                return HADES_OK;
+            }
             return merkle_reduce(ctx, leaves, per_dev, sub_levels, scratch, gathered + g * roots_per_dev * 4, d.streams[0]);
         };
         rc = step();
     }
+    auto gathered_of = [&](size_t g) { return ctx->devs[g].work + (leaf_elems + scratch_elems) * 4; };
     if (rc == HADES_OK && G > 1) {
         auto gather = [&]() -> int {
-            auto gathered_of = [&](size_t g) { return ctx->devs[g].work + (per_dev + scratch_elems) * 4; };
             if (ctx->use_nccl) {
                 NcclApi& api = nccl_api();
                 NCCL_TRY(ctx, api.GroupStart());
@@ -818,8 +823,8 @@ int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leav
         auto step = [&]() -> int {
             DeviceState& d = ctx->devs[g];
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            uint64_t* scratch = d.work + per_dev * 4;
-            uint64_t* gathered = scratch + scratch_elems * 4;
+            uint64_t* scratch = d.work + leaf_elems * 4;
+            uint64_t* gathered = gathered_of(g);
             uint64_t* result = gathered + (n_roots + 8) * 4;
             if (top_levels == 0) {
                 CUDA_TRY(ctx, cudaMemcpyAsync(result, gathered, 32, cudaMemcpyDeviceToDevice, d.streams[0]));
@@ -838,6 +843,24 @@ int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leav
         if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "merkle pass failed on device %d: %s", ctx->devs[g].ordinal, cudaGetErrorString(e));
     }
     return rc;
+}
+
+int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]) {
+    if (!ctx || !host_leaves || !root) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+    if (n_leaves == 1) {
+        memcpy(root, host_leaves, 32);
+        return HADES_OK;
+    }
+    return merkle_root_sharded(ctx, host_leaves, nullptr, n_leaves, root);
+}
+
+int hades_merkle_root_sharded_dev(hades_ctx* ctx, const uint64_t* const* d_leaves, size_t n_leaves, uint64_t root[4]) {
+    if (!ctx || !d_leaves || !root) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+    for (size_t g = 0; g < ctx->devs.size(); g++)
+        if (!d_leaves[g] || ((uintptr_t)d_leaves[g] & 15)) return fail(ctx, HADES_ERR_INVALID_ARG, "d_leaves[%zu] must be non-null and 16-byte aligned", g);
+    return merkle_root_sharded(ctx, nullptr, d_leaves, n_leaves, root);
 }
 
 // capacity word of the sponge: zero, or the caller's domain tag (a canonical field element, Montgomery limbs)

@@ -129,6 +129,13 @@ class CudaStrategy(Strategy):
                                                 root.ctypes.data_as(_native.u64p)))
         return root
 
+    def merkle_root_sharded_device(self, leaf_ptrs: Sequence[int], n_leaves: int) -> np.ndarray:
+        """root of a tree whose leaves are resident: leaf_ptrs[g] = device pointer of the g-th device's leaf range"""
+        arr = (ctypes.c_void_p * len(leaf_ptrs))(*leaf_ptrs)
+        root = np.empty(4, dtype=np.uint64)
+        self._check(self._lib.hades_merkle_root_sharded_dev(self._ctx, arr, n_leaves, root.ctypes.data_as(_native.u64p)))
+        return root
+
     def merkle_reduce_device(self, nodes_ptr: int, n_nodes: int, levels: int, scratch_ptr: int, out_ptr: int,
                              stream: int = 0, dev_index: int = 0) -> None:
         self._check(self._lib.hades_merkle_reduce_dev(self._ctx, dev_index, nodes_ptr, n_nodes, levels, scratch_ptr,

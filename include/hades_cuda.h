@@ -96,6 +96,9 @@ int hades_perm_batch_dev(hades_ctx* ctx, int dev_index, uint64_t* d_states, size
  * reference removed its Merkle code in 0.7.0, CHANGELOG.md:159-162.)
  */
 int hades_merkle_root(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]);
+/* Same with the leaves already RESIDENT: d_leaves[g] points at leaves [g n/G, (g+1) n/G) in the memory of the
+ * context's g-th device (G = hades_device_count, a power of two; >= 1024 leaves per device).  Synchronous. */
+int hades_merkle_root_sharded_dev(hades_ctx* ctx, const uint64_t* const* d_leaves, size_t n_leaves, uint64_t root[4]);
 
 /*
  * Device-resident Merkle reduction: hashes `levels` levels, n_nodes -> n_nodes / 4^levels nodes.
