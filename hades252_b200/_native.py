@@ -52,6 +52,9 @@ SIGNATURES = {
                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "hades_set_variant": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_int]),
     "hades_set_coop_threshold": (ctypes.c_int, [ctx_p, ctypes.c_size_t]),
+    "hades_fr_op_shape": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "hades_fr_op_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                       ctypes.c_void_p]),
     "hades_launch_count": (ctypes.c_uint64, [ctx_p]),
 }
 

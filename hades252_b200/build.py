@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libhades_b200.so")
 SOURCES = ["hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu",
            "hades_w3_dense.cu", "hades_w5_dense.cu", "hades_w9_dense.cu",
-           "hades_w3_ccf.cu", "hades_w5_ccf.cu", "hades_w9_ccf.cu", "hades_generic.cu"]
+           "hades_w3_ccf.cu", "hades_w5_ccf.cu", "hades_w9_ccf.cu", "hades_generic.cu", "hades_frtest.cu"]
 HEADERS = ["fr.cuh", "hades.cuh", "coop.cuh", "width_impl.cuh", "width_ops.hpp", "util_kernels.cuh", "host_tables.hpp",
            os.path.join("..", "..", "include", "hades_cuda.h")]
 _KERNEL_HDRS = ["fr.cuh", "hades.cuh", "width_impl.cuh", "width_ops.hpp"]
@@ -20,6 +20,8 @@ def _deps(src: str):
     """headers a translation unit includes (an object is rebuilt only when one of them is newer)"""
     if src == "hades_engine.cu":
         return ["fr.cuh", "host_tables.hpp", "util_kernels.cuh", "width_ops.hpp", os.path.join("..", "..", "include", "hades_cuda.h")]
+    if src == "hades_frtest.cu":
+        return ["fr.cuh", "width_ops.hpp"]
     if src == "hades_generic.cu":
         return ["fr.cuh", "hades.cuh", "width_ops.hpp"]
     if src == "hades_w5_ccf.cu":

@@ -1074,6 +1074,23 @@ int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products
     return HADES_OK;
 }
 
+int hades_fr_op_shape(int op, int* in_words, int* out_words) {
+    if (!in_words || !out_words) return HADES_ERR_INVALID_ARG;
+    return fr_test_shape(op, in_words, out_words) ? HADES_ERR_INVALID_ARG : HADES_OK;
+}
+
+int hades_fr_op_dev(hades_ctx* ctx, int dev_index, int op, const uint32_t* d_in, uint32_t* d_out, size_t n, void* stream) {
+    if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    int iw = 0, ow = 0;
+    if (fr_test_shape(op, &iw, &ow)) return fail(ctx, HADES_ERR_INVALID_ARG, "unknown field operation %d", op);
+    if (n && (!d_in || !d_out)) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    DeviceGuard guard;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    ctx->launches++;
+    CUDA_TRY(ctx, fr_test_launch(op, d_in, d_out, n, (cudaStream_t)stream));
+    return HADES_OK;
+}
+
 int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
                       int* max_threads_per_block) {
     if (!ctx || !kernel) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");

@@ -56,4 +56,8 @@ cudaError_t generic_upload_modulus();  // to the CURRENT device
 cudaError_t generic_launch_perm(uint64_t* d_states, size_t n, int width, const uint64_t* d_tables, cudaStream_t s);
 cudaError_t generic_func_attributes(cudaFuncAttributes* out);
 
+// test-only field-arithmetic kernels (hades_frtest.cu): op codes and shapes in that file
+int fr_test_shape(int op, int* in_words, int* out_words);
+cudaError_t fr_test_launch(int op, const uint32_t* d_in, uint32_t* d_out, size_t n, cudaStream_t s);
+
 }  // namespace hades

@@ -211,6 +211,21 @@ class CudaStrategy(Strategy):
         self._check(self._lib.hades_imad_peak(self._ctx, dev_index, variant, ctypes.byref(v)))
         return v.value
 
+    def fr_op(self, op: int, operands: np.ndarray) -> np.ndarray:
+        """test-only: device field routine `op` (include/hades_cuda.h) on uint32 operands [n, in_words] -> [n, out_words]"""
+        import torch
+        iw, ow = ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.hades_fr_op_shape(op, ctypes.byref(iw), ctypes.byref(ow)))
+        a = np.ascontiguousarray(operands, dtype=np.uint32)
+        if a.ndim != 2 or a.shape[1] != iw.value:
+            raise ValueError(f"op {op} takes [n, {iw.value}] uint32 words, got {a.shape}")
+        d_in = torch.from_numpy(a.view(np.int32)).cuda()
+        d_out = torch.empty((a.shape[0], ow.value), dtype=torch.int32, device="cuda")
+        self._check(self._lib.hades_fr_op_dev(self._ctx, 0, op, d_in.data_ptr(), d_out.data_ptr(), a.shape[0],
+                                              torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return d_out.cpu().numpy().view(np.uint32)
+
     def kernel_info(self, kernel: str) -> dict:
         regs, local, thr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._check(self._lib.hades_kernel_info(self._ctx, kernel.encode(), ctypes.byref(regs), ctypes.byref(local),

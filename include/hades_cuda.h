@@ -205,6 +205,12 @@ int hades_set_variant(hades_ctx* ctx, int algo, int regs);  /* HADES_ERR_INVALID
  * latency-bound below ~2^14 states (a lone `Strategy::perm`, strategies.rs:140, is a batch of one).  Width 5,
  * algo 2 only; 0 disables; default 4736 (two 16-state blocks per SM).  Results are bit-identical either way. */
 int hades_set_coop_threshold(hades_ctx* ctx, size_t max_states);
+/* Test-only: evaluate ONE device field routine of fr.cuh on n caller-supplied operand tuples (u32 limbs, device
+ * memory): op 0 fr_mul, 1 fr_add, 2 fr_sbox, 3 sqr_mont (raw 9 limbs), 4 mul_wide, 5 redc16, 6 dot_mont<4>,
+ * 7 dot_mont_plus<4>, 8 dot_mont<5>, 9 dot_mont<1>, 10..14 canon<0..4>, 15 mul_const_short<4>, 16 fr_mul_lazy.
+ * hades_fr_op_shape gives the u32 words per element on each side.  Drives tests/test_gpu_fr.py. */
+int hades_fr_op_shape(int op, int* in_words, int* out_words);
+int hades_fr_op_dev(hades_ctx* ctx, int dev_index, int op, const uint32_t* d_in, uint32_t* d_out, size_t n, void* stream);
 /* Number of kernel launches issued through this context since creation (bench's gpu_launches). */
 uint64_t hades_launch_count(const hades_ctx* ctx);
 
