@@ -12,7 +12,7 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let units = [
         "hades_engine.cu", "hades_w3.cu", "hades_w5.cu", "hades_w9.cu", "hades_w3_dense.cu", "hades_w5_dense.cu",
-        "hades_w9_dense.cu", "hades_w3_ccf.cu", "hades_w5_ccf.cu", "hades_w9_ccf.cu", "hades_generic.cu",
+        "hades_w9_dense.cu", "hades_w3_ccf.cu", "hades_w5_ccf.cu", "hades_w9_ccf.cu", "hades_generic.cu", "hades_frtest.cu",
     ];
     let mut objs = Vec::new();
     for u in units {
@@ -34,6 +34,7 @@ fn main() {
         .args(["-shared", "-cudart", "static", "-o"])
         .arg(&lib)
         .args(&objs)
+        .args(["-ldl", "-lpthread"]) // libnccl.so.2 is dlopen'ed on demand by multi-device contexts
         .status()
         .unwrap()
         .success();

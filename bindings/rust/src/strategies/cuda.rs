@@ -147,6 +147,39 @@ impl CudaStrategy {
     }
 }
 
+impl CudaStrategy {
+    /// Sponge digests with domain separation: the capacity word starts as `domain` instead of zero.
+    pub fn sponge_batch_with_domain(
+        &mut self,
+        domain: BlsScalar,
+        elems: &[BlsScalar],
+        offsets: &[u64],
+    ) -> Result<Vec<BlsScalar>, CudaError> {
+        assert!(!offsets.is_empty() && offsets[0] == 0 && *offsets.last().unwrap() as usize <= elems.len());
+        let n = offsets.len() - 1;
+        let mut out = std::vec![BlsScalar::zero(); n];
+        let rc = unsafe {
+            ffi::hades_sponge_batch_ds(
+                self.ctx,
+                elems.as_ptr() as *const u64,
+                offsets.as_ptr(),
+                n,
+                &domain as *const BlsScalar as *const u64,
+                out.as_mut_ptr() as *mut u64,
+            )
+        };
+        if rc != ffi::HADES_OK {
+            return Err(Self::error(self.ctx, rc));
+        }
+        Ok(out)
+    }
+
+    /// How a multi-device context gathers subtree roots ("ncclAllGather (NCCL x.y.z, ...)").
+    pub fn collective(&self) -> String {
+        unsafe { CStr::from_ptr(ffi::hades_collective(self.ctx)) }.to_string_lossy().into_owned()
+    }
+}
+
 impl Drop for CudaStrategy {
     fn drop(&mut self) {
         unsafe { ffi::hades_destroy(self.ctx) }

@@ -80,4 +80,22 @@ extern "C" {
     ) -> c_int;
     pub fn hades_host_register(ctx: *mut hades_ctx, ptr: *mut c_void, bytes: usize) -> c_int;
     pub fn hades_host_unregister(ctx: *mut hades_ctx, ptr: *mut c_void) -> c_int;
+    // sponge with a domain tag in the capacity word
+    pub fn hades_sponge_batch_ds(
+        ctx: *mut hades_ctx,
+        elems: *const u64,
+        offsets: *const u64,
+        n_msgs: usize,
+        domain_tag: *const u64,
+        out: *mut u64,
+    ) -> c_int;
+    // leaves resident on the context's devices: d_leaves[g] = device pointer of the g-th range
+    pub fn hades_merkle_root_sharded_dev(
+        ctx: *mut hades_ctx,
+        d_leaves: *const *const u64,
+        n_leaves: usize,
+        root: *mut u64,
+    ) -> c_int;
+    pub fn hades_set_coop_threshold(ctx: *mut hades_ctx, max_states: usize) -> c_int;
+    pub fn hades_collective(ctx: *const hades_ctx) -> *const c_char;
 }
