@@ -42,7 +42,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """One nvcc -c per translation unit (in parallel), then one link into the shared library."""
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    objdir = os.path.join(HERE, "lib", "obj")
+    # HADES_BUILD_TAG=x: an experimental build (with HADES_NVCC_EXTRA flags) beside the default one:
+    # lib/libhades_b200_x.so from lib/obj_x/, selected at run time with HADES_B200_LIB
+    tag = os.environ.get("HADES_BUILD_TAG", "")
+    lib_path = LIB.replace(".so", f"_{tag}.so") if tag else LIB
+    objdir = os.path.join(HERE, "lib", "obj" + (f"_{tag}" if tag else ""))
     os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("HADES_NVCC_EXTRA", "").split()  # e.g. -DHADES_SYNC_MID for experiments
@@ -66,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         results = list(pool.map(compile_one, SOURCES))
-    log = os.path.join(HERE, "lib", "build.log")
+    log = os.path.join(HERE, "lib", "build.log" if not tag else f"build_{tag}.log")
     with open(log, "w") as f:
         for src, obj, cmd, res in results:
             f.write(" ".join(cmd) + "\n" + res.stdout + "\n")
@@ -75,17 +79,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stdout)
         if res.returncode:
             raise RuntimeError(f"nvcc failed on {src} ({res.returncode}); see {log}")
-    if (os.path.exists(LIB) and all(getattr(r[3], "fresh", False) for r in results)
-            and all(os.path.getmtime(r[1]) <= os.path.getmtime(LIB) for r in results)):
-        return LIB
-    link = [nvcc, "-shared", "-cudart", "static", "-o", LIB, *[r[1] for r in results], "-ldl", "-lpthread"]
+    if (os.path.exists(lib_path) and all(getattr(r[3], "fresh", False) for r in results)
+            and all(os.path.getmtime(r[1]) <= os.path.getmtime(lib_path) for r in results)):
+        return lib_path
+    link = [nvcc, "-shared", "-cudart", "static", "-o", lib_path, *[r[1] for r in results], "-ldl", "-lpthread"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(log, "a") as f:
         f.write(" ".join(link) + "\n" + res.stdout)
     if res.returncode:
         sys.stderr.write(res.stdout)
         raise RuntimeError(f"link failed ({res.returncode}); see {log}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

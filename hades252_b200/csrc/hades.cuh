@@ -302,6 +302,32 @@ struct CcfLayout {
     static constexpr int kEntries = kPinv + t * (t - 1);
 };
 
+// Which operand of a constant-times-state dot product is walked by the carry chains (`vec`, 4 limbs per chain) and which
+// is consumed one limb per step (`sca`)?  The product is symmetric, so this is purely a register-allocation choice.
+// Constants reach IMAD.WIDE as uniform-register operands: with the constants as `vec` ALL 8 limbs of all N constants
+// are wanted in uniform registers for the whole dot product (N = 8 at W = 9: 64 > the 63 that exist, so ptxas falls
+// back to LDC into ordinary registers -- 379 LDC per partial round and 144 bytes of spills in the round-1 build); with
+// the constants as `sca` only N uniform values are live per step and the state limbs, which sit in registers anyway,
+// are the chain operands.  W <= 5 keeps the constants as `vec` (32 uniform registers, measured faster).
+#ifndef HADES_SWAP_FROM_W
+#define HADES_SWAP_FROM_W 9
+#endif
+template <int W>
+struct DotRoles {
+    static constexpr bool kConstIsSca = W >= HADES_SWAP_FROM_W;
+};
+// r = (t + sum_j tab[base + j] * word(j)) / R  (kInject) or without t; `word(j, limb)` yields state limbs
+template <int N, bool kSwap, bool kInject, class T, class Word>
+HADES_DEV void const_dot(uint32_t (&r)[9], int base, Word word, const uint32_t* t) {
+    if constexpr (kSwap) {
+        dot_mont_core<N, 8, kInject>(
+            r, [&](int j, int k) { return word(j, k); }, [&](int j, int i) { return T::tab(base + j, i); }, t);
+    } else {
+        dot_mont_core<N, 8, kInject>(
+            r, [&](int j, int k) { return T::tab(base + j, k); }, [&](int j, int i) { return word(j, i); }, t);
+    }
+}
+
 // r (9 limbs) += v (8 limbs)
 HADES_DEV void add_into9(uint32_t (&r)[9], const Fr& v) {
     uint32_t r8[8], lo[8];
@@ -326,8 +352,7 @@ HADES_DEV void unit_column_rows(Fr (&s)[N], int base) {
     for (int row = 0; row < ROWS; row++) {
         uint32_t r[9];
         const int b = base + row * (N - 1);
-        dot_mont<N - 1>(
-            r, [&](int j, int k) { return T::tab(b + j, k); }, [&](int j, int i) { return s[j + 1].l[i]; });
+        const_dot<N - 1, DotRoles<N>::kConstIsSca, false, T>(r, b, [&](int j, int i) { return s[j + 1].l[i]; }, nullptr);
         add_into9(r, s[0]);
         Fr res;
         canon<(N <= 5) ? 1 : 2>(res, r);
@@ -370,14 +395,12 @@ HADES_DEV void partial_round_ccf(Fr (&s)[W], int base) {
     Fr newx, neww;
     {
         uint32_t r[9];
-        dot_mont_plus<t>(
-            r, [&](int j, int k) { return T::tab(base + 1 + t + j, k); }, [&](int j, int i) { return s[j].l[i]; }, y);
+        const_dot<t, DotRoles<W>::kConstIsSca, true, T>(r, base + 1 + t, [&](int j, int i) { return s[j].l[i]; }, y);
         canon<(W <= 5) ? 1 : 2>(newx, r);
     }
     {
         uint32_t r[9];
-        dot_mont_plus<t>(
-            r, [&](int j, int k) { return T::tab(base + 1 + j, k); }, [&](int j, int i) { return s[j].l[i]; }, y);
+        const_dot<t, DotRoles<W>::kConstIsSca, true, T>(r, base + 1, [&](int j, int i) { return s[j].l[i]; }, y);
         canon<(W <= 5) ? 1 : 2>(neww, r);
     }
     // shift the words, the new one enters at the end
@@ -427,8 +450,7 @@ HADES_DEV void hades_perm_ccf(Fr (&s)[W]) {
     {
         auto dense_row = [&](Fr& res, int b) {
             uint32_t r[9];
-            dot_mont<W>(
-                r, [&](int j, int k) { return T::tab(b + j, k); }, [&](int j, int i) { return s[j].l[i]; });
+            const_dot<W, DotRoles<W>::kConstIsSca, false, T>(r, b, [&](int j, int i) { return s[j].l[i]; }, nullptr);
             canon<(W <= 6) ? 1 : 2>(res, r);
         };
         Fr out[t];
