@@ -1096,7 +1096,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
     if (!ctx || !kernel) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
     cudaFuncAttributes a;
-    cudaError_t e = ctx->generic() ? (strcmp(kernel, "perm") ? cudaErrorInvalidValue : generic_func_attributes(&a))
+    cudaError_t e = ctx->generic() ? (strcmp(kernel, "perm") ? cudaErrorInvalidValue : generic_func_attributes((int)ctx->width, &a))
                                    : ctx->ops()->func_attributes(kernel, ctx->variant, &a);
     if (e == cudaErrorInvalidValue) return fail(ctx, HADES_ERR_INVALID_ARG, "unknown kernel '%s' for width %u", kernel, ctx->width);
     CUDA_TRY(ctx, e);

@@ -1,9 +1,11 @@
-// Generic-width permutation kernel (runtime W in 2..14): the reference lets a user change WIDTH and the
-// MDS asset (README.md:30-31, assets/HOWTO.md) as long as 67*W <= 960 round constants (strategies.rs:40).
-// Tuned kernels exist for W = 3, 5, 9 (width_impl.cuh); every other width runs this one: the reference's
-// round structure (src/strategies.rs:79-157, src/strategies/scalar.rs:23-49) with the state in a
-// runtime-indexed array and the constant tables in global memory.  Correct, bit-identical, not tuned
-// (about 5x slower per multiplication than the tuned kernels).
+// Permutation kernels for the widths WITHOUT a tuned build: the reference lets a user change WIDTH and the MDS asset
+// (README.md:30-31, assets/HOWTO.md) as long as 67*W <= 960 round constants (strategies.rs:40).  Tuned kernels exist
+// for W = 3, 5, 9 (width_impl.cuh); every other width in 2..14 runs perm_dense_kernel<W> below: the reference's round
+// structure (src/strategies.rs:79-157, src/strategies/scalar.rs:23-49) compiled per width, state in registers, each
+// MDS row ONE lazily reduced W-term Montgomery dot product (fr.cuh dot_mont<W>; the reference reduces every product
+// and every addition), constants read from a per-context table in global memory with warp-uniform addresses (one
+// broadcast transaction per constant; the 64 KB constant bank is per translation unit and is left to the tuned widths).
+// Round 1 ran a single runtime-width kernel with one reduction per matrix entry, about 5x slower per multiplication.
 #include <cuda_runtime.h>
 
 #include "fr.cuh"
@@ -16,54 +18,84 @@ namespace {
 constexpr int kMaxW = 14;
 constexpr int kThreads = 128;
 
-__device__ __forceinline__ void load_fr(Fr& x, const uint32_t* p) {
-#pragma unroll
-    for (int k = 0; k < 8; k++) x.l[k] = p[k];
+// 8 limbs of table entry `e` (32-byte aligned: the table comes from cudaMalloc)
+__device__ __forceinline__ void load_entry(uint32_t (&c)[8], const uint4* __restrict__ tab, int e) {
+    const uint4 lo = __ldg(tab + 2 * e), hi = __ldg(tab + 2 * e + 1);
+    c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w;
+    c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
 }
 
-// tables: ark[67*W][8] then mds[W*W][8] (u32 limbs, Montgomery form), in global memory
-__global__ void __launch_bounds__(kThreads) perm_generic_kernel(uint32_t* __restrict__ states, size_t n, int W,
-                                                                const uint32_t* __restrict__ tables) {
-    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t* ark = tables;
-    const uint32_t* mds = tables + (size_t)kRounds * W * 8;
-    uint32_t* p = states + i * (size_t)W * 8;
-    Fr s[kMaxW], out[kMaxW];
-    for (int j = 0; j < W; j++) load_fr(s[j], p + 8 * j);
+// tables: ark[67*W] then mds[W*W], 8 u32 Montgomery limbs each
+template <int W>
+__device__ __forceinline__ void perm_dense(Fr (&s)[W], const uint4* __restrict__ tab) {
     constexpr int kHalf = kFullRounds / 2;
+    constexpr int kMds = kRounds * W;
 #pragma unroll 1
     for (int r = 0; r < kRounds; r++) {
-        for (int j = 0; j < W; j++) {  // scalar.rs:23-30
+        // add_round_key (scalar.rs:23-30)
+#pragma unroll
+        for (int j = 0; j < W; j++) {
             Fr c;
-            load_fr(c, ark + (size_t)(r * W + j) * 8);
+            load_entry(c.l, tab, r * W + j);
             fr_add(s[j], s[j], c);
         }
-        const bool full = r < kHalf || r >= kHalf + kPartialRounds;
-        for (int j = full ? 0 : W - 1; j < W; j++) {  // strategies.rs:115 / :89
-            Fr x = s[j];
-            fr_sbox(x);
-            s[j] = x;
-        }
-        for (int k = 0; k < W; k++) {  // scalar.rs:36-49
-            Fr acc;
-#pragma unroll
-            for (int q = 0; q < 8; q++) acc.l[q] = 0;
+        // S-box on every word (strategies.rs:115) or on the last one (strategies.rs:89); a real loop over a rotating
+        // register file keeps the code small
+        if (r < kHalf || r >= kHalf + kPartialRounds) {
 #pragma unroll 1
             for (int j = 0; j < W; j++) {
-                Fr m, t;
-                load_fr(m, mds + (size_t)(k * W + j) * 8);
-                fr_mul(t, m, s[j]);
-                fr_add(acc, acc, t);
+                Fr x = s[0];
+                fr_sbox(x);
+                rotate_in<W>(s, x);
             }
-            out[k] = acc;
+        } else {
+            fr_sbox(s[W - 1]);
         }
+        // mul_matrix (scalar.rs:36-49): row k = sum_j M[k][j] s_j, one reduction per row.
+        // Bound: < p (1 + 0.4528 W): W <= 6 -> < 4p, W <= 14 -> < 8p.
+        Fr out[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) out[j] = s[j];  // placeholders
+#pragma unroll 1
+        for (int row = 0; row < W; row++) {
+            uint32_t acc[9];
+            const int base = kMds + row * W;
+            // the state limbs walk the chains, the constants are consumed one limb per step (hades.cuh DotRoles): only W
+            // constant limbs are live per step, fetched as broadcast loads
+            uint32_t m[W][8];
+#pragma unroll
+            for (int j = 0; j < W; j++) load_entry(m[j], tab, base + j);
+            dot_mont<W>(acc, [&](int j, int k) { return s[j].l[k]; }, [&](int j, int i) { return m[j][i]; });
+            Fr res;
+            canon<(W <= 6) ? 1 : 2>(res, acc);
+            rotate_in<W>(out, res);
+        }
+#pragma unroll
         for (int j = 0; j < W; j++) s[j] = out[j];
     }
-    for (int j = 0; j < W; j++)
-#pragma unroll
-        for (int k = 0; k < 8; k++) p[8 * j + k] = s[j].l[k];
 }
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) perm_dense_kernel(uint4* __restrict__ states, size_t n, const uint4* __restrict__ tab) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    uint4* p = states + i * (2 * W);
+    Fr s[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        const uint4 lo = p[2 * j], hi = p[2 * j + 1];
+        s[j].l[0] = lo.x; s[j].l[1] = lo.y; s[j].l[2] = lo.z; s[j].l[3] = lo.w;
+        s[j].l[4] = hi.x; s[j].l[5] = hi.y; s[j].l[6] = hi.z; s[j].l[7] = hi.w;
+    }
+    perm_dense<W>(s, tab);
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        p[2 * j] = make_uint4(s[j].l[0], s[j].l[1], s[j].l[2], s[j].l[3]);
+        p[2 * j + 1] = make_uint4(s[j].l[4], s[j].l[5], s[j].l[6], s[j].l[7]);
+    }
+}
+
+#define HADES_GENERIC_WIDTHS(X) X(2) X(4) X(6) X(7) X(8) X(10) X(11) X(12) X(13) X(14)
 
 }  // namespace
 
@@ -71,13 +103,26 @@ cudaError_t generic_upload_modulus() { return upload_modulus(); }
 
 cudaError_t generic_launch_perm(uint64_t* d_states, size_t n, int width, const uint64_t* d_tables, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    size_t blocks = (n + kThreads - 1) / kThreads;
+    const size_t blocks = (n + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffULL || width < 2 || width > kMaxW) return cudaErrorInvalidValue;
-    perm_generic_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(reinterpret_cast<uint32_t*>(d_states), n, width,
-                                                             reinterpret_cast<const uint32_t*>(d_tables));
+    uint4* st = reinterpret_cast<uint4*>(d_states);
+    const uint4* tab = reinterpret_cast<const uint4*>(d_tables);
+    switch (width) {
+#define HADES_CASE(w) case w: perm_dense_kernel<w><<<(unsigned)blocks, kThreads, 0, s>>>(st, n, tab); break;
+        HADES_GENERIC_WIDTHS(HADES_CASE)
+#undef HADES_CASE
+        default: return cudaErrorInvalidValue;  // 3, 5, 9 have tuned kernels (width_impl.cuh)
+    }
     return cudaGetLastError();
 }
 
-cudaError_t generic_func_attributes(cudaFuncAttributes* out) { return cudaFuncGetAttributes(out, perm_generic_kernel); }
+cudaError_t generic_func_attributes(int width, cudaFuncAttributes* out) {
+    switch (width) {
+#define HADES_CASE(w) case w: return cudaFuncGetAttributes(out, perm_dense_kernel<w>);
+        HADES_GENERIC_WIDTHS(HADES_CASE)
+#undef HADES_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 }  // namespace hades

@@ -51,10 +51,10 @@ const WidthOps* width_ops_3(int algo);
 const WidthOps* width_ops_5(int algo);
 const WidthOps* width_ops_9(int algo);
 
-// generic-width kernel (hades_generic.cu): any width in 2..14, dense schedule, tables in global memory
+// widths without a tuned build (hades_generic.cu): one dense-schedule kernel per width in 2..14, tables in global memory
 cudaError_t generic_upload_modulus();  // to the CURRENT device
 cudaError_t generic_launch_perm(uint64_t* d_states, size_t n, int width, const uint64_t* d_tables, cudaStream_t s);
-cudaError_t generic_func_attributes(cudaFuncAttributes* out);
+cudaError_t generic_func_attributes(int width, cudaFuncAttributes* out);
 
 // test-only field-arithmetic kernels (hades_frtest.cu): op codes and shapes in that file
 int fr_test_shape(int op, int* in_words, int* out_words);
