@@ -78,6 +78,7 @@ def parse_args():
     ap.add_argument("--workload", default="perm", choices=["perm", "merkle", "sponge", "sweep"],
                     help="perm = BASELINE configs[1] (default, the contract line); merkle = configs[2]; "
                          "sponge = configs[3]; sweep = configs[4]")
+    ap.add_argument("--widths", default="3,5,9", help="sweep: widths (3, 5, 9 tuned; any of 2..14)")
     ap.add_argument("--log2-leaves", type=int, default=24)
     ap.add_argument("--log2-msgs", type=int, default=22)
     ap.add_argument("--verify", action="store_true", help="extras: compare against the CPU oracle (slow)")
@@ -737,7 +738,7 @@ def run_sweep(args):
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
     rows = []
-    for w in (3, 5, 9):
+    for w in [int(x) for x in args.widths.split(",")]:
         strat = CudaStrategy([local], width=w)
         for l2 in range(16, args.log2_states + 1, 2):
             n = 1 << l2

@@ -116,11 +116,11 @@ class CopyPool {
         std::unique_lock<std::mutex> lk(job.m);
         job.cv.wait(lk, [&] { return job.left.load() == 0; });
     }
-    size_t threads() const { return workers_.size(); }
-
   private:
     CopyPool() {
+        // the box's hardware threads are shared by the ranks of a torchrun job (LOCAL_WORLD_SIZE processes)
         unsigned hw = std::thread::hardware_concurrency();
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) hw = std::max(2u, hw / (unsigned)std::max(1, atoi(e)));
         if (const char* e = getenv("HADES_COPY_THREADS")) hw = (unsigned)std::max(0, atoi(e));
         const unsigned n = std::min(16u, hw);
         for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
