@@ -88,6 +88,20 @@ public:
                                  out.empty() ? nullptr : &out[0].limbs[0]));
         return out;
     }
+    // sponge with domain separation: the capacity word starts as `domain` (include/hades_cuda.h)
+    std::vector<BlsScalar> sponge_batch(const BlsScalar& domain, const std::vector<BlsScalar>& elems,
+                                        const std::vector<std::uint64_t>& offsets) {
+        if (offsets.empty() || offsets.front() != 0 || offsets.back() > elems.size())
+            throw std::invalid_argument("offsets needs n + 1 entries, offsets[0] == 0 and offsets[n] <= elems.size()");
+        std::vector<BlsScalar> out(offsets.size() - 1);
+        check(hades_sponge_batch_ds(ctx_, elems.empty() ? nullptr : &elems[0].limbs[0], offsets.data(), out.size(), domain.limbs,
+                                    out.empty() ? nullptr : &out[0].limbs[0]));
+        return out;
+    }
+    // batches of at most `max_states` states take the cooperative low-latency kernel (0 disables; default 4736)
+    void set_coop_threshold(std::size_t max_states) { check(hades_set_coop_threshold(ctx_, max_states)); }
+    std::string collective() const { return hades_collective(ctx_); }
+
     hades_ctx* raw() { return ctx_; }
 
 private:

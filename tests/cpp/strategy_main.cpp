@@ -32,6 +32,18 @@ int main(int argc, char** argv) {
         bool threw = false;
         try { strategy.perm(x.data(), 4); } catch (const std::invalid_argument&) { threw = true; }
         if (!threw) { std::puts("wrong length accepted"); return 1; }
+        // the lone perm above ran the cooperative kernel; the one-thread kernel must give the same bits
+        strategy.set_coop_threshold(0);
+        State x2;
+        x2.fill(s17);
+        strategy.perm(x2.data(), x2.size());
+        if (!(x2 == x)) { std::puts("cooperative and one-thread kernels differ"); return 1; }
+        // sponge with a zero domain tag equals the plain sponge; a non-zero tag separates the domain
+        std::vector<BlsScalar> msg = {s17, s19, s17};
+        std::vector<std::uint64_t> off = {0, 3};
+        BlsScalar zero{{0, 0, 0, 0}};
+        auto plain = strategy.sponge_batch(msg, off), tagged0 = strategy.sponge_batch(zero, msg, off), tagged = strategy.sponge_batch(s19, msg, off);
+        if (!(plain[0] == tagged0[0]) || plain[0] == tagged[0]) { std::puts("sponge domain separation failed"); return 1; }
         static_assert(Strategy<BlsScalar>::rounds() == 67, "rounds");
         std::puts("cpp strategy OK");
         return 0;
