@@ -766,21 +766,39 @@ static int merkle_root_sharded(hades_ctx* ctx, const uint64_t* host_leaves, cons
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
             int r = ensure_work(ctx, d, total_elems * 32);
             if (r) return r;
-            uint64_t* scratch = d.work + leaf_elems * 4;
-            uint64_t* gathered = scratch + scratch_elems * 4;
-            const uint64_t* leaves = d.work;
             if (host_leaves)
                 CUDA_TRY(ctx, cudaMemcpyAsync(d.work, host_leaves + g * per_dev * 4, per_dev * 32, cudaMemcpyHostToDevice, d.streams[0]));
-            else
-                leaves = d_leaves[g];
-            // own subtree roots land in their slot of the gather buffer (in-place all-gather)
-            if (sub_levels == 0) {
-                CUDA_TRY(ctx, cudaMemcpyAsync(gathered + g * roots_per_dev * 4, leaves, roots_per_dev * 32, cudaMemcpyDeviceToDevice, d.streams[0]));
-                return HADES_OK;
-            }
-            return merkle_reduce(ctx, leaves, per_dev, sub_levels, scratch, gathered + g * roots_per_dev * 4, d.streams[0]);
+            return HADES_OK;
         };
         rc = step();
+    }
+    // Levels are issued LEVEL-MAJOR (for every level: all devices), so that every device has its first, longest
+    // kernel queued after G launches instead of after (g * levels) launches of the devices before it.
+    for (int l = 0; l < std::max(sub_levels, 1) && rc == HADES_OK; l++) {
+        for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+            auto step = [&]() -> int {
+                DeviceState& d = ctx->devs[g];
+                CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+                uint64_t* scratch = d.work + leaf_elems * 4;
+                uint64_t* gathered = scratch + scratch_elems * 4;
+                const uint64_t* leaves = host_leaves ? d.work : d_leaves[g];
+                // own subtree roots land in their slot of the gather buffer (in-place all-gather)
+                uint64_t* own = gathered + g * roots_per_dev * 4;
+                if (sub_levels == 0) {
+                    CUDA_TRY(ctx, cudaMemcpyAsync(own, leaves, roots_per_dev * 32, cudaMemcpyDeviceToDevice, d.streams[0]));
+                    return HADES_OK;
+                }
+                uint64_t* bufA = scratch;
+                uint64_t* bufB = scratch + (per_dev / 4) * 4;
+                const size_t n_in = per_dev >> (2 * l), n_out = n_in / 4;
+                const uint64_t* in = l == 0 ? leaves : (((l - 1) & 1) ? bufB : bufA);
+                uint64_t* out = (l == sub_levels - 1) ? own : ((l & 1) ? bufB : bufA);
+                ctx->launches++;
+                CUDA_TRY(ctx, ctx->ops()->launch_merkle_level(ctx->variant, in, out, n_out, n_in, d.streams[0]));
+                return HADES_OK;
+            };
+            rc = step();
+        }
     }
     auto gathered_of = [&](size_t g) { return ctx->devs[g].work + (leaf_elems + scratch_elems) * 4; };
     if (rc == HADES_OK && G > 1) {
