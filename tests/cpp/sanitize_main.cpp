@@ -23,9 +23,11 @@ int main() {
         return 77;
     }
     for (int algo = 0; algo < 3; algo++)
-        for (int regs : {0, 6}) {
-            if (algo == 0 && regs == 6) continue;
-            CHECK(hades_set_variant(ctx, algo, regs));
+        for (int regs : {0, 6, 106}) {   // 106: shape 6 with the cooperative small-batch kernels switched off
+            if (algo == 0 && regs != 0) continue;
+            if (regs == 106 && algo != 2) continue;
+            CHECK(hades_set_variant(ctx, algo, regs % 100));
+            if (algo == 2) CHECK(hades_set_coop_threshold(ctx, regs == 106 ? 0 : 4736));
             for (size_t n : {1, 31, 33, 127, 129, 300}) {
                 std::vector<uint64_t> s(n * 20);
                 fill(s);
@@ -42,10 +44,20 @@ int main() {
             std::vector<uint64_t> elems((offsets[200] + 1) * 4), out(200 * 4);
             fill(elems);
             CHECK(hades_sponge_batch(ctx, elems.data(), offsets.data(), 200, out.data()));
+            uint64_t tag[4] = {7, 0, 0, 0};
+            CHECK(hades_sponge_batch_ds(ctx, elems.data(), offsets.data(), 200, tag, out.data()));
         }
+    {   // pageable memory through the pinned bounce buffers (forced: the batch is far below one chunk)
+        CHECK(hades_set_host_path(ctx, 1));
+        std::vector<uint64_t> s(1000 * 20);
+        fill(s);
+        CHECK(hades_perm_batch(ctx, s.data(), 1000));
+        CHECK(hades_copy_probe(ctx, s.data(), 1000));
+        CHECK(hades_set_host_path(ctx, 0));
+    }
     hades_destroy(ctx);
-    // other widths: tuned 3 / 9 and the generic kernel (7)
-    for (uint32_t w : {3u, 9u, 7u}) {
+    // other widths: tuned 3 / 9 and per-width dense kernels (7, 4, 12)
+    for (uint32_t w : {3u, 9u, 7u, 4u, 12u}) {
         const uint64_t* mds = w == 3 ? &HADES_MDS_MATRIX_3[0][0] : w == 9 ? &HADES_MDS_MATRIX_9[0][0] : nullptr;
         std::vector<uint64_t> fake;
         if (!mds) {  // any canonical values do for a memory check
