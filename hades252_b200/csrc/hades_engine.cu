@@ -522,6 +522,7 @@ int hades_perm_batch_dev(hades_ctx* ctx, int dev_index, uint64_t* d_states, size
     if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
     if (n == 0) return HADES_OK;
     if (!d_states || ((uintptr_t)d_states & 15)) return fail(ctx, HADES_ERR_INVALID_ARG, "d_states must be non-null and 16-byte aligned");
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     return launch_perm_w(ctx, d_states, n, (cudaStream_t)stream, &ctx->devs[dev_index]);
 }
@@ -647,6 +648,7 @@ int hades_merkle_reduce_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_nod
     if (levels > 1 && !d_scratch) return fail(ctx, HADES_ERR_INVALID_ARG, "scratch required for more than one level");
     if (((uintptr_t)d_nodes | (uintptr_t)d_out | (uintptr_t)d_scratch) & 15)
         return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     if (levels == 0) {
         CUDA_TRY(ctx, cudaMemcpyAsync(d_out, d_nodes, n_nodes * 32, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -672,6 +674,7 @@ int hades_merkle_tree_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leave
     if (n_leaves == 1) return HADES_OK;  // the leaf is the root; no interior node
     if (!d_tree) return fail(ctx, HADES_ERR_INVALID_ARG, "null tree pointer");
     if (((uintptr_t)d_leaves | (uintptr_t)d_tree) & 15) return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     const uint64_t* in = d_leaves;
     uint64_t* out = d_tree;
@@ -696,6 +699,7 @@ int hades_merkle_open_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leave
     if (!d_tree || !d_index || !d_branch) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     if (((uintptr_t)d_leaves | (uintptr_t)d_tree | (uintptr_t)d_branch) & 15)
         return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     const size_t chunks = n_open * (size_t)levels * 8;
     const unsigned blocks = (unsigned)std::min<size_t>((chunks + 255) / 256, 148 * 16);
@@ -901,13 +905,13 @@ static int sponge_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, co
     if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
     SpongeTag stag;
     if (int r = make_tag(ctx, tag, stag)) return r;
-    DeviceGuard guard;
     if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "sponge needs a width-5 context");
     if (n_msgs == 0) return HADES_OK;
     if (!d_offsets || !d_out) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     if (((uintptr_t)d_elems | (uintptr_t)d_out) & 15) return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     if (n_msgs > 0x7fffffffULL) return fail(ctx, HADES_ERR_INVALID_ARG, "too many messages for one call");
     cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     // Length bucketing: sort message indices by permutation count so that the 32 messages of a warp
     // need the same number of perms (a strictly sequential chain per message).
@@ -1012,6 +1016,7 @@ int hades_sponge_batch_ds(hades_ctx* ctx, const uint64_t* elems, const uint64_t*
 
 int hades_host_register(hades_ctx* ctx, void* ptr, size_t bytes) {
     if (!ctx || !ptr) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
     CUDA_TRY(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
     return HADES_OK;
@@ -1026,6 +1031,7 @@ int hades_gen_elems_dev(hades_ctx* ctx, int dev_index, uint64_t* d_out, uint64_t
                         uint64_t seed, void* stream) {
     if (!valid_dev(ctx, dev_index) || (!d_out && n_elems)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad argument");
     if (!n_elems) return HADES_OK;
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     size_t blocks = std::min<size_t>((n_elems * 4 + 255) / 256, 148 * 16);
     gen_elems_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_out, first_elem, n_elems, seed);
@@ -1038,6 +1044,7 @@ int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uin
                      uint64_t* d_digest, void* stream) {
     if (!valid_dev(ctx, dev_index) || !d_digest || (!d_limbs && n_limbs)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad argument");
     if (!n_limbs) return HADES_OK;
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     size_t blocks = std::min<size_t>((n_limbs + 255) / 256, 148 * 16);
     digest_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_limbs, first_limb, n_limbs,
@@ -1050,6 +1057,7 @@ int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uin
 int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products_per_s) {
     if (!valid_dev(ctx, dev_index) || !products_per_s || variant < 0 || variant > 4)
         return fail(ctx, HADES_ERR_INVALID_ARG, "bad argument");
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
     const int threads = 256, blocks = 148 * 8;
     uint32_t *d_in = nullptr, *d_out = nullptr;
@@ -1112,6 +1120,7 @@ int hades_fr_op_dev(hades_ctx* ctx, int dev_index, int op, const uint32_t* d_in,
 int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
                       int* max_threads_per_block) {
     if (!ctx || !kernel) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].ordinal));
     cudaFuncAttributes a;
     cudaError_t e = ctx->generic() ? (strcmp(kernel, "perm") ? cudaErrorInvalidValue : generic_func_attributes((int)ctx->width, &a))
