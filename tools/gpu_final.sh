@@ -9,5 +9,5 @@ python - <<'PY'
 import json
 d = json.load(open("gpurun_out/bench.json"))
 print({k: d[k] for k in ("metric", "value", "ms_per_step", "n_gpus", "gpu_launches", "oracle_sample_match", "oracle_sample_states")})
-print("e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], "roofline", {k: d["roofline"][k] for k in ("bound", "achieved", "peak", "frac", "executed_frac", "traffic")}, d["clocks"])
+print("e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], "roofline", {k: d["roofline"][k] for k in ("bound", "achieved", "peak", "frac", "frac_pipe", "frac_algorithmic", "traffic")}, d["clocks"])
 PY
