@@ -652,7 +652,20 @@ def run_merkle(args):
             torch.cuda.synchronize()
             open_ms = ev[1].elapsed_time(ev[2])
             tree_root = tree[-4:].cpu().numpy().view(np.uint64)
+            # batched verification of the same openings: 12 permutations per opening (int-mul bound)
+            okv = torch.zeros(n_open, dtype=torch.int32, device="cuda")
+            root_d = tree[-4:].clone()
+            strat.merkle_verify_device(leaves.data_ptr(), n, idx.data_ptr(), n_open, branch.data_ptr(), root_d.data_ptr(), okv.data_ptr(), sp)
+            torch.cuda.synchronize()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(stream)
+            strat.merkle_verify_device(leaves.data_ptr(), n, idx.data_ptr(), n_open, branch.data_ptr(), root_d.data_ptr(), okv.data_ptr(), sp)
+            v1.record(stream)
+            torch.cuda.synchronize()
+            verify_ms = v0.elapsed_time(v1)
             out["resident_tree"] = {"build_ms": ev[0].elapsed_time(ev[1]), "interior_nodes": nodes,
+                                    "verify": {"n_open": n_open, "ms": verify_ms, "all_verified": int(okv.sum().item()) == n_open,
+                                               "perms_per_s": n_open * levels / (verify_ms * 1e-3)},
                                     "root_equals_reduce_path": bool(np.array_equal(tree_root, root_limbs)),
                                     "openings": {"n_open": n_open, "levels": levels, "ms": open_ms,
                                                  "bytes_written": n_open * levels * 128,

@@ -96,6 +96,18 @@ extern "C" {
         n_leaves: usize,
         root: *mut u64,
     ) -> c_int;
+    pub fn hades_merkle_verify_dev(
+        ctx: *mut hades_ctx,
+        dev_index: c_int,
+        d_leaves: *const u64,
+        n_leaves: usize,
+        d_index: *const u64,
+        n_open: usize,
+        d_branch: *const u64,
+        d_root: *const u64,
+        d_ok: *mut u32,
+        stream: *mut c_void,
+    ) -> c_int;
     pub fn hades_set_coop_threshold(ctx: *mut hades_ctx, max_states: usize) -> c_int;
     pub fn hades_collective(ctx: *const hades_ctx) -> *const c_char;
 }

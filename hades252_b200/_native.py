@@ -30,6 +30,8 @@ SIGNATURES = {
     "hades_merkle_tree_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "hades_merkle_open_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "hades_merkle_verify_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "hades_merkle_root_ragged": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_size_t, u64p]),
     "hades_sponge_batch": (ctypes.c_int, [ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "hades_sponge_batch_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,

@@ -711,6 +711,25 @@ int hades_merkle_open_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leave
     return HADES_OK;
 }
 
+int hades_merkle_verify_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leaves, size_t n_leaves, const uint64_t* d_index,
+                            size_t n_open, const uint64_t* d_branch, const uint64_t* d_root, uint32_t* d_ok, void* stream) {
+    if (!valid_dev(ctx, dev_index)) return fail(ctx, HADES_ERR_INVALID_ARG, "bad context or device index");
+    if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");
+    if (n_leaves == 0 || !d_leaves) return fail(ctx, HADES_ERR_INVALID_ARG, "a tree needs at least one leaf");
+    if (n_open == 0) return HADES_OK;
+    int levels = 0;
+    for (size_t m = n_leaves; m > 1; m = (m + 3) / 4) levels++;
+    if (!d_index || !d_root || !d_ok || (levels && !d_branch)) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
+    if (((uintptr_t)d_leaves | (uintptr_t)d_branch | (uintptr_t)d_root) & 15)
+        return fail(ctx, HADES_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    DeviceGuard guard;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    ctx->launches++;
+    CUDA_TRY(ctx, ctx->ops()->launch_merkle_verify(ctx->variant, d_leaves, d_index, n_open, n_leaves, levels, d_branch, d_root, d_ok,
+                                                   (cudaStream_t)stream));
+    return HADES_OK;
+}
+
 int hades_merkle_root_ragged(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]) {
     if (!ctx || !host_leaves || !root) return fail(ctx, HADES_ERR_INVALID_ARG, "null pointer");
     if (ctx->width != 5) return fail(ctx, HADES_ERR_INVALID_ARG, "merkle needs a width-5 context");

@@ -254,6 +254,59 @@ merkle_level_lockstep_kernel(const uint4* __restrict__ in, uint4* __restrict__ o
 }
 #endif  // HADES_ALGO >= 1
 
+// ---- batched verification of Merkle openings: the consumer of hades_merkle_open_dev's branches --------------
+// One thread per opening walks its path: at every level the stored group of four children must hold the running
+// node at the path position and zeros where the (ragged) level has no child; the parent is
+// perm([2^k - 1, c_0 .. c_{k-1}, 0 ...])[1]; after the last level the node must equal the root.
+// (Build-defined like the tree itself; the checker restates it as `merkle_verify`.)
+__device__ __forceinline__ bool fr_equal(const Fr& a, const Fr& b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) d |= a.l[k] ^ b.l[k];
+    return d == 0;
+}
+__device__ __forceinline__ bool fr_is_zero(const Fr& a) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) d |= a.l[k];
+    return d == 0;
+}
+template <int ALGO, int MINB>
+__global__ void __launch_bounds__(kPermThreads, MINB)
+merkle_verify_kernel(const uint4* __restrict__ leaves, const uint64_t* __restrict__ index, size_t n_open, size_t n_leaves,
+                     int levels, const uint4* __restrict__ branch, const uint4* __restrict__ root, uint32_t* __restrict__ ok) {
+    const size_t o = (size_t)blockIdx.x * kPermThreads + threadIdx.x;
+    if (o >= n_open) return;
+    size_t i = index[o], m = n_leaves;
+    bool good = i < n_leaves;
+    if (!good) i = 0;  // keep every address in range; the verdict is already false
+    Fr node;
+    fr_load(node, leaves + i * 2);
+    const uint4* b = branch + o * (size_t)levels * 8;
+#pragma unroll 1
+    for (int l = 0; l < levels; l++) {
+        const size_t first = 4 * (i / 4);
+        const int k = m - first < 4 ? (int)(m - first) : 4;
+        const int pos = (int)(i & 3);
+        Fr s[5];
+        fr_set_mask(s[0], k);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            fr_load(s[1 + j], b + l * 8 + 2 * j);
+            if (j == pos) good &= fr_equal(s[1 + j], node);
+            if (j >= k) good &= fr_is_zero(s[1 + j]);
+        }
+        permute<ALGO>(s);
+        node = s[1];
+        i >>= 2;
+        m = (m + 3) / 4;
+    }
+    Fr r;
+    fr_load(r, root);
+    good &= (m == 1) && fr_equal(node, r);
+    ok[o] = good ? 1u : 0u;
+}
+
 // ---- sponge: rate 4 / capacity 1, one message per thread (CSR offsets) ------------------------------
 // `order` (optional) maps thread -> message so that a warp works on messages of equal block count.
 template <int ALGO, int MINB>
@@ -496,6 +549,16 @@ cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out
                    <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out, n_in));
     return cudaGetLastError();
 }
+cudaError_t launch_merkle_verify(Variant, const uint64_t* d_leaves, const uint64_t* d_index, size_t n_open, size_t n_leaves, int levels,
+                                 const uint64_t* d_branch, const uint64_t* d_root, uint32_t* d_ok, cudaStream_t s) {
+    if (n_open == 0) return cudaSuccess;
+    const size_t blocks = (n_open + kPermThreads - 1) / kPermThreads;
+    if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
+    merkle_verify_kernel<kAlgo, 4><<<(unsigned)blocks, kPermThreads, 0, s>>>(
+        reinterpret_cast<const uint4*>(d_leaves), d_index, n_open, n_leaves, levels, reinterpret_cast<const uint4*>(d_branch),
+        reinterpret_cast<const uint4*>(d_root), d_ok);
+    return cudaGetLastError();
+}
 cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
                           uint64_t* d_out, size_t n_threads, SpongeTag tag, cudaStream_t s) {
     if (n_threads == 0) return cudaSuccess;
@@ -555,6 +618,7 @@ cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* o
     if (!strcmp(kernel, "perm")) return HADES_ATTR(perm_batch_kernel, v, out);
 #if HADES_W == 5
     if (!strcmp(kernel, "merkle")) return HADES_ATTR(merkle_level_kernel, v, out);
+    if (!strcmp(kernel, "merkle_verify")) return cudaFuncGetAttributes(out, merkle_verify_kernel<kAlgo, 4>);
     if (!strcmp(kernel, "sponge")) return HADES_ATTR(sponge_kernel, v, out);
 #endif
     return cudaErrorInvalidValue;
@@ -571,9 +635,9 @@ bool supports(Variant v) {
 
 const WidthOps kOps = {W, kAlgo, (size_t)kTableEntries * 4, upload, launch_perm,
 #if HADES_W == 5
-                       launch_merkle_level, launch_sponge,
+                       launch_merkle_level, launch_sponge, launch_merkle_verify,
 #else
-                       nullptr, nullptr,
+                       nullptr, nullptr, nullptr,
 #endif
                        func_attributes, supports};
 

@@ -42,6 +42,8 @@ struct WidthOps {
     cudaError_t (*launch_merkle_level)(Variant v, const uint64_t* d_in, uint64_t* d_out, size_t n_out, size_t n_in, cudaStream_t s);
     cudaError_t (*launch_sponge)(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
                                  uint64_t* d_out, size_t n_threads, SpongeTag tag, cudaStream_t s);
+    cudaError_t (*launch_merkle_verify)(Variant v, const uint64_t* d_leaves, const uint64_t* d_index, size_t n_open, size_t n_leaves,
+                                        int levels, const uint64_t* d_branch, const uint64_t* d_root, uint32_t* d_ok, cudaStream_t s);
     cudaError_t (*func_attributes)(const char* kernel, Variant v, cudaFuncAttributes* out);
     bool (*supports)(Variant v);  // is this launch shape (regs) built for this width / schedule?
 };

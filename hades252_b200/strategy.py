@@ -164,6 +164,12 @@ class CudaStrategy(Strategy):
         self._check(self._lib.hades_merkle_open_dev(self._ctx, dev_index, leaves_ptr, tree_ptr, n_leaves, index_ptr, n_open,
                                                     branch_ptr, stream))
 
+    def merkle_verify_device(self, leaves_ptr: int, n_leaves: int, index_ptr: int, n_open: int, branch_ptr: int, root_ptr: int,
+                             ok_ptr: int, stream: int = 0, dev_index: int = 0) -> None:
+        """ok[o] (uint32) = 1 iff opening o (leaf leaves[index[o]], branch[o]) recomputes to the root at root_ptr"""
+        self._check(self._lib.hades_merkle_verify_dev(self._ctx, dev_index, leaves_ptr, n_leaves, index_ptr, n_open, branch_ptr,
+                                                      root_ptr, ok_ptr, stream))
+
     def sponge_batch(self, elems: np.ndarray, offsets: np.ndarray, domain_tag: Optional[np.ndarray] = None) -> np.ndarray:
         """Sponge digests of n messages in CSR form; elems uint64 [total, 4], offsets uint64 [n+1].
         `domain_tag` (uint64 [4], one canonical field element): initial capacity word (domain separation)."""

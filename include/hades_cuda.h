@@ -123,6 +123,7 @@ int hades_merkle_reduce_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_nod
  *                               resident tree: d_branch[o][l][c] (32 B each, l < number of levels, c < 4) =
  *                               child c of the level-(l+1) ancestor of leaf d_index[o], the path node
  *                               included, zero where the child does not exist; asynchronous on `stream`
+ *   hades_merkle_verify_dev     recomputes the root from each opening (levels permutations per opening)
  *   hades_merkle_root_ragged    HOST leaves -> root, on the context's first device
  */
 size_t hades_merkle_tree_nodes(size_t n_leaves);
@@ -131,6 +132,15 @@ int hades_merkle_tree_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leave
 int hades_merkle_open_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leaves, const uint64_t* d_tree, size_t n_leaves,
                           const uint64_t* d_index, size_t n_open, uint64_t* d_branch, void* stream);
 int hades_merkle_root_ragged(hades_ctx* ctx, const uint64_t* host_leaves, size_t n_leaves, uint64_t root[4]);
+/*
+ * Batched verification of openings (the consumer of hades_merkle_open_dev): for each of n_open openings, walk the
+ * path from leaf d_leaves[d_index[o]] up through d_branch[o][l][0..3] (same layout as hades_merkle_open_dev writes):
+ * the running node must sit at its position in every group, absent children of a ragged level must be zero, and the
+ * node after the last level must equal d_root (one element).  d_ok[o] = 1 / 0.  One thread per opening, `levels`
+ * permutations each; asynchronous on `stream`.
+ */
+int hades_merkle_verify_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_leaves, size_t n_leaves, const uint64_t* d_index,
+                            size_t n_open, const uint64_t* d_branch, const uint64_t* d_root, uint32_t* d_ok, void* stream);
 
 /*
  * Sponge hash (rate 4, capacity 1) of n_msgs variable-length messages given in CSR form:

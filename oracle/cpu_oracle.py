@@ -163,6 +163,32 @@ def merkle_opening(leaves: np.ndarray, tree: np.ndarray, index: int) -> np.ndarr
     return branch
 
 
+def merkle_verify_batch(leaf_nodes: np.ndarray, index: np.ndarray, n_leaves: int, branch: np.ndarray, root: np.ndarray) -> np.ndarray:
+    """hades_ref.merkle_verify over a batch: leaf_nodes [n, 4], index [n], branch [n, levels, 4, 4], root [4] -> bool [n].
+    Every level is one perm_batch over all openings."""
+    n = leaf_nodes.shape[0]
+    node = np.ascontiguousarray(leaf_nodes, dtype=np.uint64).copy()
+    i = np.asarray(index, dtype=np.uint64).astype(np.int64).copy()
+    good = i < n_leaves
+    i[~good] = 0
+    m = n_leaves
+    masks = np.array([hades_ref.to_mont_limbs((1 << k) - 1) for k in range(5)], dtype=np.uint64)
+    for l in range(branch.shape[1]):
+        group = branch[:, l]                                    # [n, 4, 4]
+        k = np.minimum(4, m - 4 * (i // 4))                     # present children per opening
+        pos = i % 4
+        good &= np.all(group[np.arange(n), pos] == node, axis=1)
+        for c in range(4):
+            good &= (c < k) | np.all(group[:, c] == 0, axis=1)
+        states = np.empty((n, 5, 4), dtype=np.uint64)
+        states[:, 0] = masks[k]
+        states[:, 1:] = group
+        node = perm_batch(states)[:, 1]
+        i //= 4
+        m = (m + 3) // 4
+    return good & (m == 1) & np.all(node == np.asarray(root, dtype=np.uint64)[None, :], axis=1)
+
+
 def gen_elems(first_elem: int, n_elems: int, seed: int = hades_ref.SEED) -> np.ndarray:
     out = np.empty((n_elems, 4), dtype=np.uint64)
     lib().oracle_gen_elems(_p(out), first_elem, n_elems, seed & 0xFFFFFFFFFFFFFFFF)

@@ -791,3 +791,89 @@ def test_config2_2pow26_states_strided_sample(cuda_strategy, oracle):
     assert np.array_equal(first, dig.cpu().numpy())
     del d
     torch.cuda.empty_cache()
+
+
+# ---- batched verification of openings: open -> verify round trip, tampering, oracle agreement ------------------
+@pytest.mark.parametrize("n", [1, 5, 64, 1000, 3 * 4 ** 6 + 1234])
+def test_merkle_open_verify_roundtrip_and_tampering(cuda_strategy, oracle, H, n):
+    import torch
+    leaves = oracle.gen_elems(900 + n, n)
+    tree = oracle.merkle_tree(leaves) if n > 1 else np.empty((0, 4), dtype=np.uint64)
+    root = tree[-1] if n > 1 else leaves[0]
+    levels = len(oracle.merkle_level_sizes(n))
+    rng = np.random.default_rng(n)
+    idx = np.unique(np.concatenate([[0, n - 1], rng.integers(0, n, size=min(n, 400))])).astype(np.uint64)
+    k = idx.shape[0]
+    sp = torch.cuda.current_stream().cuda_stream
+    d_leaves = torch.from_numpy(leaves.view(np.int64).copy()).cuda()
+    d_tree = torch.from_numpy(tree.view(np.int64).copy()).cuda() if n > 1 else torch.zeros(4, dtype=torch.int64, device="cuda")
+    d_idx = torch.from_numpy(idx.view(np.int64).copy()).cuda()
+    d_branch = torch.zeros((k, max(levels, 1), 4, 4), dtype=torch.int64, device="cuda")
+    d_root = torch.from_numpy(root.view(np.int64).copy()).cuda()
+    d_ok = torch.full((k,), 7, dtype=torch.int32, device="cuda")
+    cuda_strategy.merkle_open_device(d_leaves.data_ptr(), d_tree.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), sp)
+    cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), d_root.data_ptr(), d_ok.data_ptr(), sp)
+    torch.cuda.synchronize()
+    assert d_ok.cpu().numpy().tolist() == [1] * k              # every genuine opening verifies
+    if levels == 0:
+        return
+    # tamper: flip one bit of one limb somewhere in half of the branches, a wrong index in some, a wrong root for all
+    branch = d_branch.cpu().numpy().view(np.uint64).reshape(k, levels, 4, 4).copy()
+    bad = branch.copy()
+    victims = rng.choice(k, size=max(1, k // 2), replace=False)
+    for v in victims:
+        l, c, limb = rng.integers(0, levels), rng.integers(0, 4), rng.integers(0, 4)
+        bad[v, l, c, limb] ^= np.uint64(1) << np.uint64(rng.integers(0, 62))
+    bad_idx = idx.copy()
+    movers = [v for v in rng.choice(k, size=min(k, 20), replace=False) if n > 1]
+    for v in movers:
+        bad_idx[v] = (int(idx[v]) + 1) % n if n > 1 else idx[v]
+    want = oracle.merkle_verify_batch(leaves[bad_idx.astype(np.int64)], bad_idx, n, bad, root)
+    assert not want[victims].any()
+    d_bad = torch.from_numpy(bad.view(np.int64)).cuda()
+    d_bidx = torch.from_numpy(bad_idx.view(np.int64).copy()).cuda()
+    cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_bidx.data_ptr(), k, d_bad.data_ptr(), d_root.data_ptr(), d_ok.data_ptr(), sp)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_ok.cpu().numpy().astype(bool), want)
+    wrong_root = torch.from_numpy(oracle.gen_elems(1, 1)[0].view(np.int64).copy()).cuda()
+    cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), wrong_root.data_ptr(), d_ok.data_ptr(), sp)
+    torch.cuda.synchronize()
+    assert not d_ok.cpu().numpy().any()
+    # one genuine path re-verified from scratch with the big-int reference
+    o = k // 2
+    path = [[H.from_mont_limbs([int(x) for x in node]) for node in group] for group in branch[o]]
+    assert H.merkle_verify(H.from_mont_limbs([int(x) for x in leaves[int(idx[o])]]), int(idx[o]), n, path,
+                           H.from_mont_limbs([int(x) for x in root]))
+
+
+def test_merkle_open_verify_full_size_roundtrip(cuda_strategy, oracle):
+    """size-independent property at BASELINE size: resident tree over 2^24 leaves, 2^20 openings gathered on the device,
+    every one of them recomputes to the root (12 permutations each); a tampered copy fails everywhere it was touched"""
+    import torch
+    n, n_open, levels = 1 << 24, 1 << 20, 12
+    sp = torch.cuda.current_stream().cuda_stream
+    leaves = torch.empty(n * 4, dtype=torch.int64, device="cuda")
+    cuda_strategy.gen_elems_device(leaves.data_ptr(), 0, n, 0x4861646573323532, sp)
+    tree = torch.empty(cuda_strategy.merkle_tree_nodes(n) * 4, dtype=torch.int64, device="cuda")
+    cuda_strategy.merkle_tree_device(leaves.data_ptr(), n, tree.data_ptr(), sp)
+    idx = (torch.arange(n_open, dtype=torch.int64, device="cuda") * 2654435761) % n
+    branch = torch.empty(n_open * levels * 16, dtype=torch.int64, device="cuda")
+    ok = torch.zeros(n_open, dtype=torch.int32, device="cuda")
+    cuda_strategy.merkle_open_device(leaves.data_ptr(), tree.data_ptr(), n, idx.data_ptr(), n_open, branch.data_ptr(), sp)
+    root = tree[-4:].clone()
+    cuda_strategy.merkle_verify_device(leaves.data_ptr(), n, idx.data_ptr(), n_open, branch.data_ptr(), root.data_ptr(), ok.data_ptr(), sp)
+    torch.cuda.synchronize()
+    assert [hex(int(x)) for x in root.cpu().numpy().view(np.uint64)] == ["0x7695019b62c48e7e", "0xa403f682e9373c0", "0xd57e20ff7fb97d67", "0x3eab808a8f6b96a3"]
+    assert int(ok.sum().item()) == n_open
+    # flip one bit in the sibling data of every 7th opening (child (pos + 1) % 4 of level 3: never the path node itself)
+    b = branch.view(n_open, levels, 4, 4)
+    victims = torch.arange(0, n_open, 7, device="cuda")
+    pos = ((idx[victims] >> 6) & 3 + 1) % 4
+    b[victims, 3, pos, 2] ^= 1 << 17
+    cuda_strategy.merkle_verify_device(leaves.data_ptr(), n, idx.data_ptr(), n_open, branch.data_ptr(), root.data_ptr(), ok.data_ptr(), sp)
+    torch.cuda.synchronize()
+    okc = ok.bool()
+    assert not okc[victims].any()
+    mask = torch.ones(n_open, dtype=torch.bool, device="cuda")
+    mask[victims] = False
+    assert okc[mask].all()

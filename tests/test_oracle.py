@@ -231,3 +231,24 @@ def test_sponge_domain_separation_golden(golden):
     elems = C.gen_elems(3, 9)
     off = np.array([0, 4, 9], dtype=np.uint64)
     assert np.array_equal(C.sponge_batch(elems, off, domain_tag=zero), C.sponge_batch(elems, off))
+
+
+def test_merkle_verify_batch_matches_bigint_reference():
+    n = 77
+    leaves = C.gen_elems(5, n)
+    tree = C.merkle_tree(leaves)
+    idx = np.array([0, 3, 4, 63, 64, 76], dtype=np.uint64)
+    branch = np.stack([C.merkle_opening(leaves, tree, int(i)) for i in idx])
+    ok = C.merkle_verify_batch(leaves[idx.astype(np.int64)], idx, n, branch, tree[-1])
+    assert ok.all()
+    leaf_vals = [H.from_mont_limbs([int(x) for x in l]) for l in leaves]
+    root = H.from_mont_limbs([int(x) for x in tree[-1]])
+    for o, i in enumerate(idx):
+        path = [[H.from_mont_limbs([int(x) for x in node]) for node in group] for group in branch[o]]
+        assert H.merkle_verify(leaf_vals[int(i)], int(i), n, path, root)
+    bad = branch.copy()
+    bad[2, 1, 2, 0] ^= np.uint64(4)
+    ok = C.merkle_verify_batch(leaves[idx.astype(np.int64)], idx, n, bad, tree[-1])
+    assert ok.tolist() == [True, True, False, True, True, True]
+    path = [[H.from_mont_limbs([int(x) for x in node]) % H.P for node in group] for group in bad[2]]
+    assert not H.merkle_verify(leaf_vals[int(idx[2])], int(idx[2]), n, path, root)
