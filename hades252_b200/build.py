@@ -53,7 +53,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", "-o", obj, os.path.join(CSRC, src)]
+        # HADES_NVCC_EXTRA_<unit> (e.g. HADES_NVCC_EXTRA_hades_w5_ccf): flags for ONE translation unit, so that a tagged
+        # experimental build recompiles only that unit (the others are copied from the default build's objects)
+        own = os.environ.get("HADES_NVCC_EXTRA_" + src.replace(".cu", ""), "").split()
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *own, "-c", "-o", obj, os.path.join(CSRC, src)]
+        if tag and not own and not extra:
+            base = os.path.join(HERE, "lib", "obj", src.replace(".cu", ".o"))
+            if os.path.exists(base) and os.path.exists(base + ".cmd"):
+                import shutil
+                shutil.copy2(base, obj)
+                res = subprocess.CompletedProcess(cmd, 0, stdout=open(base + ".cmd").read().split("\n", 1)[1])
+                res.fresh = False
+                return src, obj, cmd, res
         stamp = obj + ".cmd"   # the command line and ptxas report of the object on disk
         fresh = (not force and os.path.exists(obj) and os.path.exists(stamp)
                  and open(stamp).readline().rstrip("\n") == " ".join(cmd)
