@@ -932,6 +932,12 @@ static int sponge_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, co
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard;
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[dev_index].ordinal));
+    if (ctx->variant.algo == 2 && n_msgs <= (size_t)ctx->variant.coop_max) {
+        // few messages: the cooperative kernel (one message per 8 lanes) needs no bucketing -- one launch, no temporaries
+        ctx->launches++;
+        CUDA_TRY(ctx, ctx->ops()->launch_sponge(ctx->variant, d_elems, d_offsets, nullptr, d_out, n_msgs, stag, st));
+        return HADES_OK;
+    }
     // Length bucketing: sort message indices by permutation count so that the 32 messages of a warp
     // need the same number of perms (a strictly sequential chain per message).
     struct AsyncBufs {  // stream-ordered temporaries, released on every exit path
@@ -952,7 +958,7 @@ static int sponge_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_elems, co
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(bufs.p[4], tmp_bytes, keys, keys_out, idx, order, n, 0, 32, st));
-    ctx->launches++;
+    ctx->launches += 2;  // the radix sort above and the sponge kernel
     CUDA_TRY(ctx, ctx->ops()->launch_sponge(ctx->variant, d_elems, d_offsets, order, d_out, n_msgs, stag, st));
     return HADES_OK;
 }

@@ -457,6 +457,51 @@ merkle_level_coop_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, 
     hades_perm_coop<CoopTab>(s, lane);
     if (live && lane == 0) fr_store(out + g * 2, s[1]);
 }
+
+// Sponge for few messages (a lone hash is the commonest call a Poseidon user makes): one message per 8-lane group,
+// no length bucketing; the four groups of a warp run the warp's maximum block count (all 32 lanes must reach every
+// shuffle), a group whose message ended earlier keeps permuting a dead state and has already captured its digest.
+__global__ void __launch_bounds__(kCoopBlock)
+sponge_coop_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offsets, uint4* __restrict__ out, size_t n_msgs,
+                   const SpongeTag tag) {
+    coop_stage_table();
+    const int lane = threadIdx.x & (kCoopLanes - 1);
+    const size_t g = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const bool live = g < n_msgs;
+    uint64_t b = live ? offsets[g] : 0, e = live ? offsets[g + 1] : 0;
+    const unsigned my_blocks = live ? (unsigned)((e - b) / 4 + 1) : 0u;
+    unsigned trips = my_blocks;
+    trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 8));
+    trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 16));
+    Fr s[5], digest;
+#pragma unroll
+    for (int j = 0; j < 5; j++) fr_set_zero(s[j]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[0].l[k] = tag.l[k];
+    fr_set_zero(digest);
+    bool padded = false;
+#pragma unroll 1
+    for (unsigned trip = 0; trip < trips; trip++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            Fr x;
+            bool add = true;
+            if (b < e) {
+                fr_load(x, elems + b * 2);  // the 8 lanes of the group read the same element (broadcast)
+                b++;
+            } else if (!padded) {
+                fr_set_one(x);
+                padded = true;
+            } else {
+                add = false;
+            }
+            if (add) fr_add(s[1 + k], s[1 + k], x);
+        }
+        hades_perm_coop<CoopTab>(s, lane);
+        if (trip + 1 == my_blocks) digest = s[1];
+    }
+    if (live && lane == 0) fr_store(out + g * 2, digest);
+}
 #endif  // cooperative kernels
 
 // ---- host-side launchers ---------------------------------------------------------------------------
@@ -562,6 +607,14 @@ cudaError_t launch_merkle_verify(Variant, const uint64_t* d_leaves, const uint64
 cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_offsets, const uint32_t* d_order,
                           uint64_t* d_out, size_t n_threads, SpongeTag tag, cudaStream_t s) {
     if (n_threads == 0) return cudaSuccess;
+#if HADES_ALGO == 2
+    if (n_threads <= (size_t)v.coop_max) {  // few messages: 8 lanes per message (latency kernel), no bucketing needed
+        const unsigned blocks = (unsigned)((n_threads + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
+        sponge_coop_kernel<<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(reinterpret_cast<const uint4*>(d_elems), d_offsets,
+                                                                      reinterpret_cast<uint4*>(d_out), n_threads, tag);
+        return cudaGetLastError();
+    }
+#endif
     // lockstep shapes do not apply (messages differ in length); the optimised kernel fits 96 registers, so
     // use 5 blocks/SM (measured: 225 ms vs 249 ms at 4 blocks/SM for the 2^22-message config)
 #if HADES_ALGO >= 1
@@ -591,6 +644,7 @@ cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* o
 #if HADES_W == 5 && HADES_ALGO == 2
     if (!strcmp(kernel, "perm_coop")) return cudaFuncGetAttributes(out, perm_batch_coop_kernel);
     if (!strcmp(kernel, "merkle_coop")) return cudaFuncGetAttributes(out, merkle_level_coop_kernel);
+    if (!strcmp(kernel, "sponge_coop")) return cudaFuncGetAttributes(out, sponge_coop_kernel);
 #endif
 #if HADES_ALGO >= 1
     if (!strcmp(kernel, "perm") && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);

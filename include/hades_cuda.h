@@ -210,7 +210,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
  * with at most 128/168/255/96 registers per thread, 4/5 = lockstep blocks of 256/512 threads, 6.. = lockstep
  * 128-thread blocks (the default; see hades252_b200/csrc/width_ops.hpp). */
 int hades_set_variant(hades_ctx* ctx, int algo, int regs);  /* HADES_ERR_INVALID_ARG for a shape not built for the width */
-/* Small-batch path: batches (and Merkle levels) of at most `max_states` states run the cooperative kernels --
+/* Small-batch path: batches, Merkle levels and sponge calls of at most `max_states` states / messages run the cooperative kernels --
  * one state per group of 8 lanes, 2.1x lower latency (125 us) than the one-thread-per-state kernel, which is
  * latency-bound below ~2^14 states (a lone `Strategy::perm`, strategies.rs:140, is a batch of one).  Width 5,
  * algo 2 only; 0 disables; default 4736 (two 16-state blocks per SM).  Results are bit-identical either way. */

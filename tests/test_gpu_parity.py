@@ -877,3 +877,26 @@ def test_merkle_open_verify_full_size_roundtrip(cuda_strategy, oracle):
     mask = torch.ones(n_open, dtype=torch.bool, device="cuda")
     mask[victims] = False
     assert okc[mask].all()
+
+
+def test_coop_sponge_few_messages(oracle):
+    """few messages run sponge_coop_kernel (one message per 8 lanes, no bucketing): same digests as the oracle and as the
+    bucketed one-thread kernel (threshold 0), with and without a domain tag; a lone hash is one launch"""
+    from hades252_b200 import CudaStrategy
+    rng = np.random.default_rng(77)
+    for n in (1, 3, 4, 5, 33, 700, 4736):
+        lens = rng.integers(0, 41, size=n)
+        lens[: min(n, 3)] = [0, 4, 40][: min(n, 3)]
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        elems = oracle.gen_elems(50 + n, int(offsets[-1]))
+        want = oracle.sponge_batch(elems, offsets)
+        tag = oracle.gen_elems(9, 1)[0]
+        want_tag = oracle.sponge_batch(elems, offsets, domain_tag=tag)
+        with CudaStrategy([0]) as s:
+            assert s.kernel_info("sponge_coop")["local_bytes"] == 0
+            l0 = s.launch_count
+            assert np.array_equal(s.sponge_batch(elems, offsets), want)
+            assert s.launch_count == l0 + 1
+            assert np.array_equal(s.sponge_batch(elems, offsets, domain_tag=tag), want_tag)
+            s.set_coop_threshold(0)
+            assert np.array_equal(s.sponge_batch(elems, offsets), want)
