@@ -502,6 +502,44 @@ sponge_coop_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__
     }
     if (live && lane == 0) fr_store(out + g * 2, digest);
 }
+
+// Verification of few openings (a lone verify is a chain of `levels` permutations): one opening per 8-lane group.
+__global__ void __launch_bounds__(kCoopBlock)
+merkle_verify_coop_kernel(const uint4* __restrict__ leaves, const uint64_t* __restrict__ index, size_t n_open, size_t n_leaves,
+                          int levels, const uint4* __restrict__ branch, const uint4* __restrict__ root, uint32_t* __restrict__ ok) {
+    coop_stage_table();
+    const int lane = threadIdx.x & (kCoopLanes - 1);
+    const size_t o = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const bool live = o < n_open;
+    size_t i = live ? index[o] : 0, m = n_leaves;
+    bool good = live && i < n_leaves;
+    if (!good) i = 0;
+    Fr node;
+    fr_load(node, leaves + i * 2);
+    const uint4* b = branch + (live ? o : 0) * (size_t)levels * 8;
+#pragma unroll 1
+    for (int l = 0; l < levels; l++) {  // `levels` is uniform: every lane of the warp reaches every shuffle
+        const size_t first = 4 * (i / 4);
+        const int k = m - first < 4 ? (int)(m - first) : 4;
+        const int pos = (int)(i & 3);
+        Fr s[5];
+        fr_set_mask(s[0], k);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            fr_load(s[1 + j], b + l * 8 + 2 * j);
+            if (j == pos) good &= fr_equal(s[1 + j], node);
+            if (j >= k) good &= fr_is_zero(s[1 + j]);
+        }
+        hades_perm_coop<CoopTab>(s, lane);
+        node = s[1];
+        i >>= 2;
+        m = (m + 3) / 4;
+    }
+    Fr r;
+    fr_load(r, root);
+    good &= (m == 1) && fr_equal(node, r);
+    if (live && lane == 0) ok[o] = good ? 1u : 0u;
+}
 #endif  // cooperative kernels
 
 // ---- host-side launchers ---------------------------------------------------------------------------
@@ -594,9 +632,20 @@ cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out
                    <<<(unsigned)blocks, kPermThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out, n_in));
     return cudaGetLastError();
 }
-cudaError_t launch_merkle_verify(Variant, const uint64_t* d_leaves, const uint64_t* d_index, size_t n_open, size_t n_leaves, int levels,
+cudaError_t launch_merkle_verify(Variant v, const uint64_t* d_leaves, const uint64_t* d_index, size_t n_open, size_t n_leaves, int levels,
                                  const uint64_t* d_branch, const uint64_t* d_root, uint32_t* d_ok, cudaStream_t s) {
     if (n_open == 0) return cudaSuccess;
+#if HADES_ALGO == 2
+    if (n_open <= (size_t)v.coop_max) {  // few openings: 8 lanes per opening (latency kernel)
+        const unsigned cblocks = (unsigned)((n_open + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
+        merkle_verify_coop_kernel<<<cblocks, kCoopBlock, kCoopSmemBytes, s>>>(
+            reinterpret_cast<const uint4*>(d_leaves), d_index, n_open, n_leaves, levels, reinterpret_cast<const uint4*>(d_branch),
+            reinterpret_cast<const uint4*>(d_root), d_ok);
+        return cudaGetLastError();
+    }
+#else
+    (void)v;
+#endif
     const size_t blocks = (n_open + kPermThreads - 1) / kPermThreads;
     if (blocks > 0x7fffffffULL) return cudaErrorInvalidValue;
     merkle_verify_kernel<kAlgo, 4><<<(unsigned)blocks, kPermThreads, 0, s>>>(

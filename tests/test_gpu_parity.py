@@ -814,7 +814,13 @@ def test_merkle_open_verify_roundtrip_and_tampering(cuda_strategy, oracle, H, n)
     cuda_strategy.merkle_open_device(d_leaves.data_ptr(), d_tree.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), sp)
     cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), d_root.data_ptr(), d_ok.data_ptr(), sp)
     torch.cuda.synchronize()
-    assert d_ok.cpu().numpy().tolist() == [1] * k              # every genuine opening verifies
+    assert d_ok.cpu().numpy().tolist() == [1] * k              # every genuine opening verifies (cooperative kernel: k <= 4736)
+    cuda_strategy.set_coop_threshold(0)                        # ... and on the one-thread kernel
+    d_ok.fill_(7)
+    cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), d_root.data_ptr(), d_ok.data_ptr(), sp)
+    torch.cuda.synchronize()
+    cuda_strategy.set_coop_threshold(4736)
+    assert d_ok.cpu().numpy().tolist() == [1] * k
     if levels == 0:
         return
     # tamper: flip one bit of one limb somewhere in half of the branches, a wrong index in some, a wrong root for all
