@@ -906,3 +906,34 @@ def test_coop_sponge_few_messages(oracle):
             assert np.array_equal(s.sponge_batch(elems, offsets, domain_tag=tag), want_tag)
             s.set_coop_threshold(0)
             assert np.array_equal(s.sponge_batch(elems, offsets), want)
+
+
+def test_kernel_choice_never_changes_the_bits(oracle):
+    """hypothesis: any batch size around the cooperative threshold, any threshold, device-resident or host call -- the
+    launcher picks the cooperative or the one-thread kernel and the outputs are the oracle's either way"""
+    import torch
+    from hypothesis import given, settings, strategies as st
+    from hades252_b200 import CudaStrategy
+    pool = oracle.gen_elems(2024, 5 * 6000).reshape(6000, 5, 4)
+    want_all = oracle.perm_batch(pool)
+    strat = CudaStrategy([0])
+    try:
+        @settings(max_examples=40, deadline=None)
+        @given(n=st.integers(1, 6000), thr=st.sampled_from([0, 1, 7, 8, 9, 4735, 4736, 4737, 6000]), first=st.integers(0, 100),
+               host=st.booleans())
+        def check(n, thr, first, host):
+            n = min(n, 6000 - first)
+            strat.set_coop_threshold(thr)
+            s = pool[first:first + n].copy()
+            if host:
+                strat.perm_batch(s)
+                got = s
+            else:
+                d = torch.from_numpy(s.view(np.int64)).cuda()
+                strat.perm_batch_device(d.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                got = d.cpu().numpy().view(np.uint64).reshape(n, 5, 4)
+            assert np.array_equal(got, want_all[first:first + n])
+        check()
+    finally:
+        strat.close()
