@@ -96,7 +96,7 @@ class CopyPool {
     static CopyPool& get() { static CopyPool p; return p; }
     // dst <- src, split over the workers; returns when every byte has been copied
     void copy(void* dst, const void* src, size_t bytes) {
-        const size_t kSlice = (size_t)4 << 20;
+        const size_t kSlice = (size_t)1 << 19;
         const size_t n = std::max<size_t>(1, std::min<size_t>(workers_.size(), (bytes + kSlice - 1) / kSlice));
         if (n == 1 || workers_.empty()) { memcpy(dst, src, bytes); return; }
         struct Job { std::atomic<size_t> left; std::mutex m; std::condition_variable cv; } job;
@@ -535,10 +535,14 @@ int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
     const size_t state_bytes = (size_t)ctx->width * 32;
     const size_t G = ctx->devs.size();
     size_t chunk_states = std::max<size_t>(kPermThreads, kChunkBytes / state_bytes / kPermThreads * kPermThreads);
-    // Medium batches: split into kNumBuf chunks so that H2D, kernel and D2H still overlap.  Small batches
-    // (under kMinSplitBytes per chunk) go as ONE chunk: a launch is one latency-bound wave whatever its size up to
-    // ~16k states, so splitting would only serialise several such waves.
-    constexpr size_t kMinSplitBytes = (size_t)8 << 20;
+    // Medium batches (at least kMinSplitBytes per chunk) are split into kNumBuf chunks so that H2D, kernel and D2H --
+    // and, for pageable memory, the staging copies -- overlap.  Smaller batches go as ONE chunk: a launch is one
+    // latency-bound wave whatever its size up to ~16k states, so splitting would only add launches.
+    // (HADES_MIN_SPLIT_BYTES overrides the threshold: measurement knob.)
+    static const size_t kMinSplitBytes = [] {
+        const char* e = getenv("HADES_MIN_SPLIT_BYTES");
+        return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)1 << 20;
+    }();
     const size_t per_dev = (n + G - 1) / G;
     if (per_dev < chunk_states * kNumBuf) {
         if (per_dev * state_bytes >= kMinSplitBytes * kNumBuf)
