@@ -791,17 +791,85 @@ static int merkle_root_sharded(hades_ctx* ctx, const uint64_t* host_leaves, cons
         auto step = [&]() -> int {
             DeviceState& d = ctx->devs[g];
             CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            int r = ensure_work(ctx, d, total_elems * 32);
-            if (r) return r;
-            if (host_leaves)
-                CUDA_TRY(ctx, cudaMemcpyAsync(d.work, host_leaves + g * per_dev * 4, per_dev * 32, cudaMemcpyHostToDevice, d.streams[0]));
-            return HADES_OK;
+            return ensure_work(ctx, d, total_elems * 32);
         };
         rc = step();
     }
+    // Leaves coming from the host: the upload is pipelined with the FIRST level (which holds 3/4 of all permutations):
+    // the range of every device is cut into chunks, chunk c is uploaded on stream c % kNumBuf -- from page-locked memory
+    // directly, from pageable memory through the pinned bounce buffers filled by the copy pool -- and hashed to its
+    // level-1 nodes on the same stream while the next chunks are still in flight.  Chunk-major over the devices.
+    int first_level = 0;  // levels < first_level have been issued by the upload pipeline
+    if (rc == HADES_OK && host_leaves) {
+        constexpr size_t kLeafChunk = (size_t)1 << 19;  // leaves per chunk (16 MB): a multiple of 4
+        const bool chunked = sub_levels >= 1 && per_dev >= 2 * kLeafChunk;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, host_leaves) == cudaSuccess &&
+                            (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (!chunked) {
+            for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+                auto step = [&]() -> int {
+                    DeviceState& d = ctx->devs[g];
+                    CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+                    CUDA_TRY(ctx, cudaMemcpyAsync(d.work, host_leaves + g * per_dev * 4, per_dev * 32, cudaMemcpyHostToDevice, d.streams[0]));
+                    return HADES_OK;
+                };
+                rc = step();
+            }
+        } else {
+            const size_t n_chunks = per_dev / kLeafChunk;  // per_dev is 4^a or 2 * 4^a >= 2^20: an exact multiple
+            std::vector<char> bounce_used(G * kNumBuf, 0);
+            for (size_t g = 0; g < G && rc == HADES_OK && !pinned; g++) {
+                cudaSetDevice(ctx->devs[g].ordinal);
+                rc = ensure_bounce(ctx, ctx->devs[g], kLeafChunk * 32);
+            }
+            for (size_t c = 0; c < n_chunks && rc == HADES_OK; c++)
+                for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+                    auto step = [&]() -> int {
+                        DeviceState& d = ctx->devs[g];
+                        const int b = (int)(c % kNumBuf);
+                        CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+                        uint64_t* leaves = d.work + c * kLeafChunk * 4;
+                        const uint64_t* src = host_leaves + (g * per_dev + c * kLeafChunk) * 4;
+                        if (pinned) {
+                            CUDA_TRY(ctx, cudaMemcpyAsync(leaves, src, kLeafChunk * 32, cudaMemcpyHostToDevice, d.streams[b]));
+                        } else {
+                            if (bounce_used[g * kNumBuf + b]) CUDA_TRY(ctx, cudaEventSynchronize(d.done[b]));  // its H2D has drained
+                            CopyPool::get().copy(d.bounce[b], src, kLeafChunk * 32);
+                            CUDA_TRY(ctx, cudaMemcpyAsync(leaves, d.bounce[b], kLeafChunk * 32, cudaMemcpyHostToDevice, d.streams[b]));
+                            CUDA_TRY(ctx, cudaEventRecord(d.done[b], d.streams[b]));
+                            bounce_used[g * kNumBuf + b] = 1;
+                        }
+                        // level 1 of this chunk: scratch buffer A (or the device's root slot when the range has one level)
+                        uint64_t* scratch = d.work + leaf_elems * 4;
+                        uint64_t* gathered = scratch + scratch_elems * 4;
+                        uint64_t* out = (sub_levels == 1 ? gathered + g * roots_per_dev * 4 : scratch) + c * (kLeafChunk / 4) * 4;
+                        ctx->launches++;
+                        CUDA_TRY(ctx, ctx->ops()->launch_merkle_level(ctx->variant, leaves, out, kLeafChunk / 4, kLeafChunk, d.streams[b]));
+                        return HADES_OK;
+                    };
+                    rc = step();
+                }
+            // the remaining levels run on stream 0: it waits for the other upload streams
+            for (size_t g = 0; g < G && rc == HADES_OK; g++) {
+                auto step = [&]() -> int {
+                    DeviceState& d = ctx->devs[g];
+                    CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+                    for (int b = 1; b < kNumBuf; b++) {
+                        CUDA_TRY(ctx, cudaEventRecord(d.done[b], d.streams[b]));
+                        CUDA_TRY(ctx, cudaStreamWaitEvent(d.streams[0], d.done[b], 0));
+                    }
+                    return HADES_OK;
+                };
+                rc = step();
+            }
+            first_level = 1;
+        }
+    }
     // Levels are issued LEVEL-MAJOR (for every level: all devices), so that every device has its first, longest
     // kernel queued after G launches instead of after (g * levels) launches of the devices before it.
-    for (int l = 0; l < std::max(sub_levels, 1) && rc == HADES_OK; l++) {
+    for (int l = first_level; l < std::max(sub_levels, 1) && rc == HADES_OK; l++) {
         for (size_t g = 0; g < G && rc == HADES_OK; g++) {
             auto step = [&]() -> int {
                 DeviceState& d = ctx->devs[g];
