@@ -1070,34 +1070,108 @@ static int sponge_host(hades_ctx* ctx, const uint64_t* elems, const uint64_t* of
     }
     int rc = HADES_OK;
     DeviceGuard guard;
-    for (size_t g = 0; g < G && rc == HADES_OK; g++) {  // every device is issued before any is waited for
-        auto step = [&]() -> int {
-            DeviceState& d = ctx->devs[g];
-            const size_t m0 = bound[g], cnt = bound[g + 1] - bound[g];
-            if (!cnt) return HADES_OK;
-            const uint64_t e0 = offsets[m0], ne = offsets[m0 + cnt] - e0;
-            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
-            // persistent scratch: elements | digests | offsets
-            const size_t elems_u64 = std::max<uint64_t>(ne, 1) * 4, out_u64 = cnt * 4;
-            int r = ensure_work(ctx, d, (elems_u64 + out_u64 + cnt + 1) * 8);
-            if (r) return r;
-            uint64_t* d_elems = d.work;
-            uint64_t* d_out = d_elems + elems_u64;
-            uint64_t* d_offsets = d_out + out_u64;
-            if (ne) CUDA_TRY(ctx, cudaMemcpyAsync(d_elems, elems + e0 * 4, ne * 32, cudaMemcpyHostToDevice, d.streams[0]));
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_offsets, offsets + m0, (cnt + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
-            // offsets stay absolute: bias the element base pointer by the range's first offset
-            r = sponge_dev(ctx, (int)g, d_elems - e0 * 4, d_offsets, cnt, d_out, tag, d.streams[0]);
-            if (r) return r;
-            CUDA_TRY(ctx, cudaMemcpyAsync(out + m0 * 4, d_out, cnt * 32, cudaMemcpyDeviceToHost, d.streams[0]));
+    // Large ranges are PIPELINED: the range of a device is cut into chunks of at most kChunkElems elements / kChunkMsgs
+    // messages; chunk c is staged into pinned buffer c % kNumBuf (elements | offsets) by the copy pool, uploaded, bucketed and
+    // hashed on stream c % kNumBuf, and its digests come back through the same pinned buffer while the next chunks are in
+    // flight.  A range that fits one chunk keeps the single-shot path (lowest latency for small calls).
+    constexpr uint64_t kChunkElems = (uint64_t)1 << 21;  // 64 MB of elements
+    constexpr size_t kChunkMsgs = (size_t)1 << 19;
+    auto single_shot = [&](size_t g, size_t m0, size_t cnt) -> int {
+        DeviceState& d = ctx->devs[g];
+        if (!cnt) return HADES_OK;
+        const uint64_t e0 = offsets[m0], ne = offsets[m0 + cnt] - e0;
+        CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+        // persistent scratch: elements | digests | offsets
+        const size_t elems_u64 = std::max<uint64_t>(ne, 1) * 4, out_u64 = cnt * 4;
+        int r = ensure_work(ctx, d, (elems_u64 + out_u64 + cnt + 1) * 8);
+        if (r) return r;
+        uint64_t* d_elems = d.work;
+        uint64_t* d_out = d_elems + elems_u64;
+        uint64_t* d_offsets = d_out + out_u64;
+        if (ne) CUDA_TRY(ctx, cudaMemcpyAsync(d_elems, elems + e0 * 4, ne * 32, cudaMemcpyHostToDevice, d.streams[0]));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_offsets, offsets + m0, (cnt + 1) * 8, cudaMemcpyHostToDevice, d.streams[0]));
+        // offsets stay absolute: bias the element base pointer by the range's first offset
+        r = sponge_dev(ctx, (int)g, d_elems - e0 * 4, d_offsets, cnt, d_out, tag, d.streams[0]);
+        if (r) return r;
+        CUDA_TRY(ctx, cudaMemcpyAsync(out + m0 * 4, d_out, cnt * 32, cudaMemcpyDeviceToHost, d.streams[0]));
+        return HADES_OK;
+    };
+    auto pipelined = [&](size_t g, const std::vector<size_t>& cut) -> int {  // cut: chunk boundaries (message indices)
+        DeviceState& d = ctx->devs[g];
+        CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+        // one slot per in-flight chunk, identical layout on the device and in the pinned buffer: elements | offsets | digests
+        const size_t elems_u64 = kChunkElems * 4 + 40 * 4, off_u64 = kChunkMsgs + 8, out_u64 = kChunkMsgs * 4;
+        const size_t slot_u64 = (elems_u64 + off_u64 + out_u64 + 1) & ~(size_t)1;  // 16-byte aligned slots
+        int r = ensure_work(ctx, d, slot_u64 * 8 * kNumBuf);
+        if (r == HADES_OK) r = ensure_bounce(ctx, d, slot_u64 * 8);
+        if (r) return r;
+        const size_t n_chunks = cut.size() - 1;
+        auto drain = [&](size_t c) -> int {  // digests of chunk c: pinned buffer -> caller
+            const int b = (int)(c % kNumBuf);
+            CUDA_TRY(ctx, cudaEventSynchronize(d.done[b]));
+            const size_t m0 = cut[c], cnt = cut[c + 1] - cut[c];
+            CopyPool::get().copy(out + m0 * 4, d.bounce[b] + elems_u64 + off_u64, cnt * 32);
             return HADES_OK;
         };
-        rc = step();
+        for (size_t c = 0; c < n_chunks; c++) {
+            const int b = (int)(c % kNumBuf);
+            if (c >= (size_t)kNumBuf) {
+                r = drain(c - kNumBuf);
+                if (r) return r;
+            }
+            const size_t m0 = cut[c], cnt = cut[c + 1] - cut[c];
+            const uint64_t e0 = offsets[m0], ne = offsets[m0 + cnt] - e0;
+            uint64_t* h = d.bounce[b];
+            uint64_t* dev = d.work + (size_t)b * slot_u64;
+            if (ne) CopyPool::get().copy(h, elems + e0 * 4, ne * 32);
+            memcpy(h + elems_u64, offsets + m0, (cnt + 1) * 8);
+            if (ne) CUDA_TRY(ctx, cudaMemcpyAsync(dev, h, ne * 32, cudaMemcpyHostToDevice, d.streams[b]));
+            CUDA_TRY(ctx, cudaMemcpyAsync(dev + elems_u64, h + elems_u64, (cnt + 1) * 8, cudaMemcpyHostToDevice, d.streams[b]));
+            r = sponge_dev(ctx, (int)g, dev - e0 * 4, dev + elems_u64, cnt, dev + elems_u64 + off_u64, tag, d.streams[b]);
+            if (r) return r;
+            CUDA_TRY(ctx, cudaMemcpyAsync(h + elems_u64 + off_u64, dev + elems_u64 + off_u64, cnt * 32, cudaMemcpyDeviceToHost, d.streams[b]));
+            CUDA_TRY(ctx, cudaEventRecord(d.done[b], d.streams[b]));
+        }
+        for (size_t c = n_chunks > (size_t)kNumBuf ? n_chunks - kNumBuf : 0; c < n_chunks; c++) {
+            r = drain(c);
+            if (r) return r;
+        }
+        return HADES_OK;
+    };
+    // chunk boundaries of every device range
+    std::vector<std::vector<size_t>> cuts(G);
+    for (size_t g = 0; g < G; g++) {
+        cuts[g].push_back(bound[g]);
+        size_t start = bound[g];
+        for (size_t m = bound[g]; m < bound[g + 1]; m++) {
+            const uint64_t len = offsets[m + 1] - offsets[m];
+            if (len > kChunkElems) { cuts[g].assign({bound[g], bound[g + 1]}); break; }  // a giant message: single shot
+            if (m > start && (offsets[m + 1] - offsets[start] > kChunkElems || m - start >= kChunkMsgs)) {
+                cuts[g].push_back(m);
+                start = m;
+            }
+        }
+        if (cuts[g].back() != bound[g + 1]) cuts[g].push_back(bound[g + 1]);
     }
+    std::vector<int> rcs(G, HADES_OK);
+    std::vector<std::thread> th;
+    auto run = [&](size_t g) {
+        cudaSetDevice(ctx->devs[g].ordinal);
+        rcs[g] = cuts[g].size() > 2 ? pipelined(g, cuts[g]) : single_shot(g, bound[g], bound[g + 1] - bound[g]);
+    };
+    for (size_t g = 1; g < G; g++) {
+        if (cuts[g].size() > 2) th.emplace_back(run, g);  // a pipelined range blocks on its staging copies: own thread
+        else run(g);
+    }
+    run(0);
+    for (auto& t : th) t.join();
+    for (int r : rcs) if (r != HADES_OK && rc == HADES_OK) rc = r;
     for (size_t g = 0; g < G; g++) {
         cudaSetDevice(ctx->devs[g].ordinal);
-        cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[0]);
-        if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "sponge pass failed: %s", cudaGetErrorString(e));
+        for (int b = 0; b < kNumBuf; b++) {
+            cudaError_t e = cudaStreamSynchronize(ctx->devs[g].streams[b]);
+            if (e != cudaSuccess && rc == HADES_OK) rc = fail(ctx, HADES_ERR_CUDA, "sponge pass failed: %s", cudaGetErrorString(e));
+        }
     }
     return rc;
 }

@@ -937,3 +937,22 @@ def test_kernel_choice_never_changes_the_bits(oracle):
         check()
     finally:
         strat.close()
+
+
+def test_sponge_host_path_pipelined_chunks(cuda_strategy, oracle):
+    """hades_sponge_batch on a host batch larger than one staging chunk (2^21 elements / 2^19 messages): the range is
+    cut into chunks that are staged, uploaded, hashed and read back on rotating streams -- same digests as the oracle,
+    incl. empty messages at the chunk edges and one message longer than the others"""
+    rng = np.random.default_rng(4)
+    n = 330000
+    lens = rng.integers(0, 33, size=n)
+    lens[[0, 1, n - 1]] = 0
+    lens[n // 2] = 5000
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    assert int(offsets[-1]) > 2 * (1 << 21)
+    elems = oracle.gen_elems(31, int(offsets[-1]))
+    got = cuda_strategy.sponge_batch(elems, offsets)
+    assert np.array_equal(got, oracle.sponge_batch(elems, offsets))
+    tag = oracle.gen_elems(77, 1)[0]
+    got = cuda_strategy.sponge_batch(elems[: int(offsets[200000])], offsets[:200001], domain_tag=tag)
+    assert np.array_equal(got, oracle.sponge_batch(elems[: int(offsets[200000])], offsets[:200001], domain_tag=tag))
