@@ -75,9 +75,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", default=None, help="algo,regs kernel variant (default: library default)")
-    ap.add_argument("--workload", default="perm", choices=["perm", "merkle", "sponge", "sweep"],
+    ap.add_argument("--workload", default="perm", choices=["perm", "merkle", "sponge", "sweep", "latency"],
                     help="perm = BASELINE configs[1] (default, the contract line); merkle = configs[2]; "
-                         "sponge = configs[3]; sweep = configs[4]")
+                         "sponge = configs[3]; sweep = configs[4]; latency = small-batch latency table (1 GPU)")
     ap.add_argument("--widths", default="3,5,9", help="sweep: widths (3, 5, 9 tuned; any of 2..14)")
     ap.add_argument("--log2-leaves", type=int, default=24)
     ap.add_argument("--log2-msgs", type=int, default=22)
@@ -788,6 +788,58 @@ def run_sweep(args):
         dist.destroy_process_group()
 
 
+def run_latency(args):
+    """Small batches (a lone `Strategy::perm` is a batch of one): device-resident launch and host call, with the
+    cooperative 8-lanes-per-state kernels (default below 4737 states) and with one thread per state."""
+    import numpy as np
+    torch, dist, world, rank, local = _dist_setup()
+    from hades252_b200 import CudaStrategy
+    s = CudaStrategy([local])
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    nmax = 1 << 16
+    buf = torch.empty(nmax * 20, dtype=torch.int64, device="cuda")
+    s.gen_elems_device(buf.data_ptr(), 0, nmax * 5, SEED, sp)
+    host = buf.cpu().numpy().view(np.uint64).reshape(nmax, 5, 4)
+
+    def dev_us(n, reps=20):
+        for _ in range(3):
+            s.perm_batch_device(buf.data_ptr(), n, sp)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            s.perm_batch_device(buf.data_ptr(), n, sp)
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e3
+
+    def host_us(n, reps=10):
+        h = host[:n].copy()
+        s.perm_batch(h)
+        t = time.perf_counter()
+        for _ in range(reps):
+            s.perm_batch(h)
+        return (time.perf_counter() - t) / reps * 1e6
+
+    rows = []
+    for n in (1, 32, 1024, 2368, 4736, 8192, 16384, 65536):
+        s.set_coop_threshold(4736)
+        d1, h1 = dev_us(n), host_us(n)
+        s.set_coop_threshold(0)
+        d0, h0 = dev_us(n), host_us(n)
+        rows.append({"states": n, "device_us_default": d1, "host_call_us_default": h1,
+                     "device_us_one_thread_per_state": d0, "host_call_us_one_thread_per_state": h0})
+    if rank == 0:
+        emit({"metric": "hades252_small_batch_latency_us", "unit": "us", "n_gpus": 1, "data": "synthetic", "higher_is_better": False,
+              "config": {"workload": "small-batch latency of perm_batch (device-resident launch, CUDA events; host call on pageable memory)",
+                         "cooperative_kernel": "perm_batch_coop_kernel, one state per 8 lanes, default for <= 4736 states"},
+              "value": rows[0]["device_us_default"], "rows": rows, "kernel_info": s.kernel_info("perm_coop")})
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -823,6 +875,8 @@ def main():
         run_sponge(args)
     elif args.workload == "sweep":
         run_sweep(args)
+    elif args.workload == "latency":
+        run_latency(args)
     else:
         run_ours(args)
 
