@@ -956,3 +956,38 @@ def test_sponge_host_path_pipelined_chunks(cuda_strategy, oracle):
     tag = oracle.gen_elems(77, 1)[0]
     got = cuda_strategy.sponge_batch(elems[: int(offsets[200000])], offsets[:200001], domain_tag=tag)
     assert np.array_equal(got, oracle.sponge_batch(elems[: int(offsets[200000])], offsets[:200001], domain_tag=tag))
+
+
+def test_new_entry_points_reject_bad_arguments(cuda_strategy):
+    """argument errors of the round-2 entry points come back as status codes, never as crashes"""
+    import ctypes
+    import torch
+    from hades252_b200 import CudaStrategy, HadesError, _native
+    L = _native.lib()
+    ctx = cuda_strategy._ctx
+    d = torch.zeros(64, dtype=torch.int64, device="cuda")
+    ok = torch.zeros(4, dtype=torch.int32, device="cuda")
+    # merkle_verify: null pointers, misaligned pointers, zero leaves
+    assert L.hades_merkle_verify_dev(ctx, 0, None, 16, d.data_ptr(), 1, d.data_ptr(), d.data_ptr(), ok.data_ptr(), None) == 1
+    assert L.hades_merkle_verify_dev(ctx, 0, d.data_ptr(), 0, d.data_ptr(), 1, d.data_ptr(), d.data_ptr(), ok.data_ptr(), None) == 1
+    assert L.hades_merkle_verify_dev(ctx, 0, d.data_ptr() + 8, 16, d.data_ptr(), 1, d.data_ptr(), d.data_ptr(), ok.data_ptr(), None) == 1
+    assert L.hades_merkle_verify_dev(ctx, 0, d.data_ptr(), 16, None, 1, d.data_ptr(), d.data_ptr(), ok.data_ptr(), None) == 1
+    assert L.hades_merkle_verify_dev(ctx, 9, d.data_ptr(), 16, d.data_ptr(), 1, d.data_ptr(), d.data_ptr(), ok.data_ptr(), None) == 1
+    assert L.hades_merkle_verify_dev(ctx, 0, d.data_ptr(), 16, d.data_ptr(), 0, d.data_ptr(), d.data_ptr(), ok.data_ptr(), None) == 0  # nothing to do
+    # sharded resident root: a single-device context cannot shard
+    arr = (ctypes.c_void_p * 1)(d.data_ptr())
+    root = np.zeros(4, dtype=np.uint64)
+    assert L.hades_merkle_root_sharded_dev(ctx, arr, 12, root.ctypes.data_as(_native.u64p)) == 2      # not a power of 4
+    assert L.hades_merkle_root_sharded_dev(ctx, None, 16, root.ctypes.data_as(_native.u64p)) == 1
+    # field-op helper: unknown op, null pointers
+    iw, ow = ctypes.c_int(), ctypes.c_int()
+    assert L.hades_fr_op_shape(99, ctypes.byref(iw), ctypes.byref(ow)) == 1
+    assert L.hades_fr_op_dev(ctx, 0, 99, d.data_ptr(), d.data_ptr(), 1, None) == 1
+    assert L.hades_fr_op_dev(ctx, 0, 0, None, d.data_ptr(), 1, None) == 1
+    # host path knob and cooperative threshold
+    assert L.hades_set_host_path(ctx, 3) == 1
+    with CudaStrategy([0], width=3) as s3:
+        with pytest.raises(HadesError):
+            s3.set_coop_threshold(100)      # cooperative kernels exist for width 5 only
+    assert L.hades_copy_probe(None, None, 1) == 1
+    assert b"" == L.hades_collective(None) and cuda_strategy.collective.startswith("none")
