@@ -202,15 +202,14 @@ HADES_DEV void coop_full_round(Fr (&s)[5], int lane, int ark, int mat) {
     s[4] = outC;
 }
 
-// partial round q (table entries base = {e, alpha[4], c[4]}): see the file header
+// partial round q (table entries base = {e, alpha[4], c[4]}): see the file header.
+// The round constant is folded one round ahead: on entry s[4] already contains e_q (the caller adds e_0), and the
+// round adds e_{q+1} (table entry `next_e`, < 0 after the last round) to the new x.  Everything that does not depend on
+// the S-box output is finished while lane 0 is still multiplying: the two dot-product sums (c.w + e_{q+1} in lanes 0..3,
+// alpha.w in lanes 4..7) are canonicalised before slot 2, so that after slot 2 only  "+ x^5, two conditional
+// subtractions" is left on the critical path, once per lane half; the halves then swap their results.
 template <class T>
-HADES_DEV void coop_partial_round(Fr (&s)[5], int lane, int base) {
-    {
-        Fr e;
-#pragma unroll
-        for (int k = 0; k < 8; k++) e.l[k] = T::tab(base, k);
-        fr_add(s[4], s[4], e);
-    }
+HADES_DEV void coop_partial_round(Fr (&s)[5], int lane, int base, int next_e) {
     // slot 0: lane 0: x*x | lanes 1..3: c_j * w_j (j = lane - 1) | lanes 4..7: alpha_j * w_j (j = lane - 4)
     const int j0 = lane == 0 ? 4 : (lane < 4 ? lane - 1 : lane - 4);
     uint32_t a[8], b[8], r0[8], r1[8], r2[8];
@@ -238,27 +237,36 @@ HADES_DEV void coop_partial_round(Fr (&s)[5], int lane, int base) {
     }
     coop_butterfly(v, 1);
     coop_butterfly(v, 2);
-    uint32_t o[9];
+    // lanes 0..3: + e_{q+1}; then canonical (< 4 * 1.4528 p + p < 8 p), still off the critical path
+    if (next_e >= 0) {
+        uint32_t e[8];
 #pragma unroll
-    for (int k = 0; k < 9; k++) o[k] = v[k];
-    coop_shfl_xor_n(o, 9, 4);
-    uint32_t sc[9], sa[9];  // c . w and alpha . w (each < 4 * 1.4528 p), in every lane
-#pragma unroll
-    for (int k = 0; k < 9; k++) { sc[k] = lane < 4 ? v[k] : o[k]; sa[k] = lane < 4 ? o[k] : v[k]; }
+        for (int k = 0; k < 8; k++) e[k] = lane < 4 ? T::tab(next_e, k) : 0u;
+        coop_acc8(v, e);
+    }
+    Fr pre;
+    canon<2>(pre, v);
     // slot 2: lane 0: x^4 * x (others idle)
 #pragma unroll
     for (int k = 0; k < 8; k++) { a[k] = lane == 0 ? r1[k] : 0u; b[k] = s[4].l[k]; }
     coop_mmul(r2, a, b);
     coop_shfl_n(r2, 8, 0);  // y = x^5 / gauge, < 1.886 p, to every lane
-    coop_acc8(sc, r2);      // < 7.7 p
-    coop_acc8(sa, r2);
-    Fr newx, neww;
-    canon<2>(newx, sc);
-    canon<2>(neww, sa);
+    uint32_t sum[9];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum[k] = pre.l[k];
+    sum[8] = 0;
+    coop_acc8(sum, r2);  // < 2.886 p
+    Fr mine, other;
+    canon<1>(mine, sum);  // lanes 0..3: the new x (+ e_{q+1}), lanes 4..7: the new w
+    other = mine;
+    coop_shfl_xor_n(other.l, 8, 4);
 #pragma unroll
     for (int i = 0; i < 3; i++) s[i] = s[i + 1];
-    s[3] = neww;
-    s[4] = newx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        s[3].l[k] = lane < 4 ? other.l[k] : mine.l[k];
+        s[4].l[k] = lane < 4 ? mine.l[k] : other.l[k];
+    }
 }
 
 // back to the original basis after the partial rounds: z_i = w_0 + sum_{j=1..3} tab[pinv + 3 i + j - 1] w_j (i < 4)
@@ -294,7 +302,14 @@ HADES_DEV void hades_perm_coop(Fr (&s)[5], int lane) {
 #if !HADES_EMUL
 #pragma unroll 1
 #endif
-            for (int q = 0; q < kPartialRounds; q++) coop_partial_round<T>(s, lane, L::kPart + q * L::kPartStride);
+            {
+                Fr e;
+#pragma unroll
+                for (int k = 0; k < 8; k++) e.l[k] = T::tab(L::kPart, k);
+                fr_add(s[4], s[4], e);
+            }
+            for (int q = 0; q < kPartialRounds; q++)
+                coop_partial_round<T>(s, lane, L::kPart + q * L::kPartStride, q + 1 < kPartialRounds ? L::kPart + (q + 1) * L::kPartStride : -1);
             coop_pinv_stage<T>(s, lane, L::kPinv);
         }
     }
