@@ -790,7 +790,8 @@ def run_sweep(args):
 
 def run_latency(args):
     """Small batches (a lone `Strategy::perm` is a batch of one): device-resident launch and host call, with the
-    cooperative 8-lanes-per-state kernels (default below 4737 states) and with one thread per state."""
+    cooperative kernels (default: a warp per state up to 592 states, 8 lanes per state up to 4736), with the 8-lane
+    kernel only, and with one thread per state."""
     import numpy as np
     torch, dist, world, rank, local = _dist_setup()
     from hades252_b200 import CudaStrategy
@@ -825,16 +826,21 @@ def run_latency(args):
     rows = []
     for n in (1, 32, 1024, 2368, 4736, 8192, 16384, 65536):
         s.set_coop_threshold(4736)
+        s.set_coop_wide_threshold(592)
         d1, h1 = dev_us(n), host_us(n)
+        s.set_coop_wide_threshold(0)
+        d8 = dev_us(n)
         s.set_coop_threshold(0)
         d0, h0 = dev_us(n), host_us(n)
-        rows.append({"states": n, "device_us_default": d1, "host_call_us_default": h1,
+        rows.append({"states": n, "device_us_default": d1, "host_call_us_default": h1, "device_us_8_lanes_per_state": d8,
                      "device_us_one_thread_per_state": d0, "host_call_us_one_thread_per_state": h0})
     if rank == 0:
         emit({"metric": "hades252_small_batch_latency_us", "unit": "us", "n_gpus": 1, "data": "synthetic", "higher_is_better": False,
               "config": {"workload": "small-batch latency of perm_batch (device-resident launch, CUDA events; host call on pageable memory)",
-                         "cooperative_kernel": "perm_batch_coop_kernel, one state per 8 lanes, default for <= 4736 states"},
-              "value": rows[0]["device_us_default"], "rows": rows, "kernel_info": s.kernel_info("perm_coop")})
+                         "cooperative_kernel": "perm_batch_coop_kernel<32> (a warp per state) for <= 592 states, "
+                                               "perm_batch_coop_kernel<8> (8 lanes per state) for <= 4736 states"},
+              "value": rows[0]["device_us_default"], "rows": rows, "kernel_info": s.kernel_info("perm_coop"),
+              "kernel_info_wide": s.kernel_info("perm_coop_wide")})
     s.close()
     if world > 1:
         dist.destroy_process_group()

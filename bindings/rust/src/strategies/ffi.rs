@@ -109,5 +109,6 @@ extern "C" {
         stream: *mut c_void,
     ) -> c_int;
     pub fn hades_set_coop_threshold(ctx: *mut hades_ctx, max_states: usize) -> c_int;
+    pub fn hades_set_coop_wide_threshold(ctx: *mut hades_ctx, max_states: usize) -> c_int;
     pub fn hades_collective(ctx: *const hades_ctx) -> *const c_char;
 }

@@ -54,6 +54,7 @@ SIGNATURES = {
                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "hades_set_variant": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_int]),
     "hades_set_coop_threshold": (ctypes.c_int, [ctx_p, ctypes.c_size_t]),
+    "hades_set_coop_wide_threshold": (ctypes.c_int, [ctx_p, ctypes.c_size_t]),
     "hades_fr_op_shape": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "hades_fr_op_dev": (ctypes.c_int, [ctx_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                        ctypes.c_void_p]),

@@ -41,6 +41,9 @@ constexpr size_t kChunkBytes = (size_t)96 << 20;  // target bytes per pipeline c
 // Measured (profiles/r02_latency_small_batches.txt): 127 us up to 2368 states (one 16-state block per SM), 178 us up to
 // 4736, 333 us at 8192 -- against 269 us for the one-thread kernel at any size up to 16 384.
 constexpr int kDefaultCoopMax = 4736;
+// ... and up to this many the warp-per-state version (one block of four states per SM): 97 us instead of 111 us for a
+// lone permutation, slower than the 8-lane kernel beyond one block per SM
+constexpr int kDefaultCoopWideMax = 592;
 
 struct DeviceState {
     int ordinal = 0;
@@ -450,7 +453,10 @@ int hades_init(hades_ctx** out, const int* devices, int n_dev, uint32_t width, c
             if (ctx->has_sparse || ctx->has_ccf) {
                 ctx->variant.algo = ctx->has_ccf ? 2 : 1;
                 ctx->variant.regs = width == 9 ? 7 : 6;  // lockstep 128-thread blocks: x7 (W=3), x5 (W=5), x3 (W=9) per SM
-                if (ctx->has_ccf && width == 5) ctx->variant.coop_max = kDefaultCoopMax;
+                if (ctx->has_ccf && width == 5) {
+                    ctx->variant.coop_max = kDefaultCoopMax;
+                    ctx->variant.coop_wide_max = kDefaultCoopWideMax;
+                }
             }
         }
     }
@@ -1324,6 +1330,14 @@ int hades_set_coop_threshold(hades_ctx* ctx, size_t max_states) {
     if (ctx->width != 5 || !ctx->has_ccf)
         return fail(ctx, HADES_ERR_INVALID_ARG, "the cooperative kernels exist for width 5 with the canonical-form tables only");
     ctx->variant.coop_max = (int)std::min<size_t>(max_states, (size_t)1 << 24);
+    return HADES_OK;
+}
+
+int hades_set_coop_wide_threshold(hades_ctx* ctx, size_t max_states) {
+    if (!ctx) return fail(ctx, HADES_ERR_INVALID_ARG, "null context");
+    if (ctx->width != 5 || !ctx->has_ccf)
+        return fail(ctx, HADES_ERR_INVALID_ARG, "the cooperative kernels exist for width 5 with the canonical-form tables only");
+    ctx->variant.coop_wide_max = (int)std::min<size_t>(max_states, (size_t)1 << 24);
     return HADES_OK;
 }
 

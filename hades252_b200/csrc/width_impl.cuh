@@ -418,10 +418,12 @@ __device__ __forceinline__ void coop_stage_table() {
     __syncthreads();
 }
 
+// G = lanes per state: kCoopLanes (8) or kCoopWide (a warp; lowest latency, a quarter of the states per block)
+template <int G>
 __global__ void __launch_bounds__(kCoopBlock) perm_batch_coop_kernel(uint4* __restrict__ states, size_t n) {
     coop_stage_table();
-    const int lane = threadIdx.x & (kCoopLanes - 1);
-    const size_t g = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const int lane = threadIdx.x & (G - 1);
+    const size_t g = (size_t)blockIdx.x * (kCoopBlock / G) + (threadIdx.x / G);
     const bool live = g < n;
     Fr s[5];
     const uint4* p = states + (live ? g : 0) * 10;  // all lanes of the group read the same 160 bytes (broadcast)
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kCoopBlock) perm_batch_coop_kernel(uint4* __re
         if (live) fr_load(s[j], p + 2 * j);
         else fr_set_zero(s[j]);
     }
-    hades_perm_coop<CoopTab>(s, lane);
+    hades_perm_coop<CoopTab, G>(s, lane);
     if (live && lane < 5) {  // lane j writes word j
         Fr w;
         coop_select_word<5>(w.l, s, lane);
@@ -438,11 +440,12 @@ __global__ void __launch_bounds__(kCoopBlock) perm_batch_coop_kernel(uint4* __re
     }
 }
 
+template <int G>
 __global__ void __launch_bounds__(kCoopBlock)
 merkle_level_coop_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_out, size_t n_in) {
     coop_stage_table();
-    const int lane = threadIdx.x & (kCoopLanes - 1);
-    const size_t g = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const int lane = threadIdx.x & (G - 1);
+    const size_t g = (size_t)blockIdx.x * (kCoopBlock / G) + (threadIdx.x / G);
     const bool live = g < n_out;
     const size_t first_child = 4 * (live ? g : 0);
     const int present = !live ? 0 : (n_in - first_child < 4 ? (int)(n_in - first_child) : 4);
@@ -454,7 +457,7 @@ merkle_level_coop_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, 
         if (j < present) fr_load(s[1 + j], p + 2 * j);
         else fr_set_zero(s[1 + j]);
     }
-    hades_perm_coop<CoopTab>(s, lane);
+    hades_perm_coop<CoopTab, G>(s, lane);
     if (live && lane == 0) fr_store(out + g * 2, s[1]);
 }
 
@@ -567,9 +570,15 @@ cudaError_t upload(const uint64_t* table) {
 cudaError_t launch_perm(Variant v, uint64_t* d_states, size_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
 #if HADES_W == 5 && HADES_ALGO == 2
-    if (n <= (size_t)v.coop_max) {  // small batch: 8 lanes per state (latency kernel)
+    if (n <= (size_t)v.coop_max) {  // small batch: 8 lanes, or a whole warp, per state (latency kernels)
+        if (n <= (size_t)v.coop_wide_max) {
+            constexpr int kPer = kCoopBlock / kCoopWide;
+            perm_batch_coop_kernel<kCoopWide><<<(unsigned)((n + kPer - 1) / kPer), kCoopBlock, kCoopSmemBytes, s>>>(
+                reinterpret_cast<uint4*>(d_states), n);
+            return cudaGetLastError();
+        }
         const unsigned blocks = (unsigned)((n + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
-        perm_batch_coop_kernel<<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(reinterpret_cast<uint4*>(d_states), n);
+        perm_batch_coop_kernel<kCoopLanes><<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(reinterpret_cast<uint4*>(d_states), n);
         return cudaGetLastError();
     }
 #endif
@@ -611,9 +620,15 @@ cudaError_t launch_merkle_level(Variant v, const uint64_t* d_in, uint64_t* d_out
     if (n_out == 0) return cudaSuccess;
     if (n_in > 4 * n_out || n_in + 3 < 4 * n_out) return cudaErrorInvalidValue;  // n_out == ceil(n_in / 4)
 #if HADES_ALGO == 2
-    if (n_out <= (size_t)v.coop_max) {  // small level: 8 lanes per node (latency kernel)
+    if (n_out <= (size_t)v.coop_max) {  // small level: 8 lanes, or a whole warp, per node (latency kernels)
+        if (n_out <= (size_t)v.coop_wide_max) {
+            constexpr int kPer = kCoopBlock / kCoopWide;
+            merkle_level_coop_kernel<kCoopWide><<<(unsigned)((n_out + kPer - 1) / kPer), kCoopBlock, kCoopSmemBytes, s>>>(
+                reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out, n_in);
+            return cudaGetLastError();
+        }
         const unsigned blocks = (unsigned)((n_out + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
-        merkle_level_coop_kernel<<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(
+        merkle_level_coop_kernel<kCoopLanes><<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(
             reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), n_out, n_in);
         return cudaGetLastError();
     }
@@ -691,8 +706,10 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
 
 cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* out) {
 #if HADES_W == 5 && HADES_ALGO == 2
-    if (!strcmp(kernel, "perm_coop")) return cudaFuncGetAttributes(out, perm_batch_coop_kernel);
-    if (!strcmp(kernel, "merkle_coop")) return cudaFuncGetAttributes(out, merkle_level_coop_kernel);
+    if (!strcmp(kernel, "perm_coop")) return cudaFuncGetAttributes(out, perm_batch_coop_kernel<kCoopLanes>);
+    if (!strcmp(kernel, "merkle_coop")) return cudaFuncGetAttributes(out, merkle_level_coop_kernel<kCoopLanes>);
+    if (!strcmp(kernel, "perm_coop_wide")) return cudaFuncGetAttributes(out, perm_batch_coop_kernel<kCoopWide>);
+    if (!strcmp(kernel, "merkle_coop_wide")) return cudaFuncGetAttributes(out, merkle_level_coop_kernel<kCoopWide>);
     if (!strcmp(kernel, "sponge_coop")) return cudaFuncGetAttributes(out, sponge_coop_kernel);
 #endif
 #if HADES_ALGO >= 1

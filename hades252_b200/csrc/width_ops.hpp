@@ -23,6 +23,9 @@ struct Variant {
     // Batches (and Merkle levels) of at most this many states run the cooperative 8-lanes-per-state kernels
     // (coop.cuh; width 5, algo 2 only); 0 disables them.  hades_set_coop_threshold.
     int coop_max = 0;
+    // ... and batches / levels of at most this many states (and <= coop_max) the warp-per-state version of them
+    // (perm and Merkle level only); 0 disables it.  hades_set_coop_wide_threshold.
+    int coop_wide_max = 0;
 };
 constexpr int kPermThreads = 128;
 

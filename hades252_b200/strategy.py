@@ -248,6 +248,11 @@ class CudaStrategy(Strategy):
         (width 5, algo 2; 0 disables; bit-identical results)."""
         self._check(self._lib.hades_set_coop_threshold(self._ctx, max_states))
 
+    def set_coop_wide_threshold(self, max_states: int) -> None:
+        """Batches / Merkle levels of at most `max_states` states (within the threshold above) use a whole warp per
+        state (lowest latency; default 592, 0 disables; bit-identical results)."""
+        self._check(self._lib.hades_set_coop_wide_threshold(self._ctx, max_states))
+
     def copy_probe_ptr(self, host_ptr: int, n: int) -> None:
         """perm_batch's host pipeline without the kernel (bare H2D + D2H ceiling)."""
         self._check(self._lib.hades_copy_probe(self._ctx, host_ptr, n))

@@ -201,7 +201,8 @@ int hades_digest_dev(hades_ctx* ctx, int dev_index, const uint64_t* d_limbs, uin
  * Instruction forms validated in tools/microbench.cu. */
 int hades_imad_peak(hades_ctx* ctx, int dev_index, int variant, double* products_per_s);
 /* Registers per thread / local (spill) bytes / max threads per block of the context's current kernel
- * variant: kernel = "perm" | "merkle" | "sponge" (the last two for width 5). */
+ * variant: kernel = "perm" | "merkle" | "sponge" (the last two for width 5), and for the cooperative small-batch
+ * kernels of width 5 "perm_coop" | "merkle_coop" | "sponge_coop" | "perm_coop_wide" | "merkle_coop_wide". */
 int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, int* local_bytes,
                       int* max_threads_per_block);
 /* Select the kernel variant (all bit-identical): algo 0 = dense schedule (the reference's round
@@ -215,6 +216,11 @@ int hades_set_variant(hades_ctx* ctx, int algo, int regs);  /* HADES_ERR_INVALID
  * latency-bound below ~2^14 states (a lone `Strategy::perm`, strategies.rs:140, is a batch of one).  Width 5,
  * algo 2 only; 0 disables; default 4736 (two 16-state blocks per SM).  Results are bit-identical either way. */
 int hades_set_coop_threshold(hades_ctx* ctx, size_t max_states);
+/* Batches and Merkle levels of at most `max_states` states (and within the threshold above) give each state a whole
+ * warp instead of 8 lanes: all matrix products of a full round and all dot products of a partial round fit one slot
+ * each.  Lowest latency for a lone permutation, a quarter of the capacity per block; default 592 (one block of four
+ * states per SM), 0 disables.  Bit-identical results. */
+int hades_set_coop_wide_threshold(hades_ctx* ctx, size_t max_states);
 /* Test-only: evaluate ONE device field routine of fr.cuh on n caller-supplied operand tuples (u32 limbs, device
  * memory): op 0 fr_mul, 1 fr_add, 2 fr_sbox, 3 sqr_mont (raw 9 limbs), 4 mul_wide, 5 redc16, 6 dot_mont<4>,
  * 7 dot_mont_plus<4>, 8 dot_mont<5>, 9 dot_mont<1>, 10..14 canon<0..4>, 15 mul_const_short<4>, 16 fr_mul_lazy.

@@ -100,6 +100,8 @@ public:
     }
     // batches of at most `max_states` states take the cooperative low-latency kernel (0 disables; default 4736)
     void set_coop_threshold(std::size_t max_states) { check(hades_set_coop_threshold(ctx_, max_states)); }
+    // ... and of at most `max_states` states the warp-per-state version of it (0 disables; default 592)
+    void set_coop_wide_threshold(std::size_t max_states) { check(hades_set_coop_wide_threshold(ctx_, max_states)); }
     std::string collective() const { return hades_collective(ctx_); }
 
     hades_ctx* raw() { return ctx_; }

@@ -23,11 +23,15 @@ int main() {
         return 77;
     }
     for (int algo = 0; algo < 3; algo++)
-        for (int regs : {0, 6, 106}) {   // 106: shape 6 with the cooperative small-batch kernels switched off
+        for (int regs : {0, 6, 106, 206}) {   // 106: shape 6 with the cooperative small-batch kernels switched off,
+                                              // 206: with the 8-lane kernels only (no warp-per-state kernel)
             if (algo == 0 && regs != 0) continue;
-            if (regs == 106 && algo != 2) continue;
+            if (regs >= 100 && algo != 2) continue;
             CHECK(hades_set_variant(ctx, algo, regs % 100));
-            if (algo == 2) CHECK(hades_set_coop_threshold(ctx, regs == 106 ? 0 : 4736));
+            if (algo == 2) {
+                CHECK(hades_set_coop_threshold(ctx, regs == 106 ? 0 : 4736));
+                CHECK(hades_set_coop_wide_threshold(ctx, regs == 206 ? 0 : 592));
+            }
             for (size_t n : {1, 31, 33, 127, 129, 300}) {
                 std::vector<uint64_t> s(n * 20);
                 fill(s);

@@ -83,10 +83,10 @@ static int check_perm(int iters) {
     return 0;
 }
 
-// ---- cooperative kernel (coop.cuh): 8 host threads play the 8 lanes of a group; a shuffle is an exchange
-// through a shared array between two barriers
+// ---- cooperative kernels (coop.cuh): G host threads play the G lanes of a group (8, or a whole warp); a shuffle is
+// an exchange through a shared array between two barriers
 static pthread_barrier_t g_bar;
-static uint32_t g_xchg[8][16];
+static uint32_t g_xchg[32][16];
 static thread_local int tl_lane;
 namespace hades {
 int coop_emul_lane() { return tl_lane; }
@@ -101,28 +101,29 @@ void coop_emul_exchange(uint32_t* v, int n, int xmask, int abs_src) {
 }
 }  // namespace hades
 
+template <int G>
 static int check_coop(int iters) {
-    pthread_barrier_init(&g_bar, nullptr, 8);
+    pthread_barrier_init(&g_bar, nullptr, G);
     for (int it = 0; it < iters; it++) {
         uint64_t st[20];
         for (int j = 0; j < 5; j++) rand_fr(st + 4 * j, it < 40 ? (it + j) % 5 : 0);
-        hades::Fr s0[5], res[8][5];
+        hades::Fr s0[5], res[G][5];
         for (int j = 0; j < 5; j++) to32(s0[j], st + 4 * j);
-        std::thread th[8];
-        for (int l = 0; l < 8; l++)
+        std::thread th[G];
+        for (int l = 0; l < G; l++)
             th[l] = std::thread([&, l]() {
                 tl_lane = l;
                 hades::Fr s[5];
                 for (int j = 0; j < 5; j++) s[j] = s0[j];
-                hades::hades_perm_coop<HostTabCcf<5>>(s, l);
+                hades::hades_perm_coop<HostTabCcf<5>, G>(s, l);
                 for (int j = 0; j < 5; j++) res[l][j] = s[j];
             });
-        for (int l = 0; l < 8; l++) th[l].join();
+        for (int l = 0; l < G; l++) th[l].join();
         oracle_perm(st, 5, g_ark.data(), g_mds[5].data());
-        for (int l = 0; l < 8; l++)
+        for (int l = 0; l < G; l++)
             for (int j = 0; j < 5; j++) {
                 uint64_t got[4]; to64(got, res[l][j]);
-                if (memcmp(got, st + 4 * j, 32)) { printf("perm_coop mismatch iter %d lane %d word %d\n", it, l, j); return 1; }
+                if (memcmp(got, st + 4 * j, 32)) { printf("perm_coop<%d> mismatch iter %d lane %d word %d\n", G, it, l, j); return 1; }
             }
     }
     pthread_barrier_destroy(&g_bar);
@@ -182,7 +183,8 @@ int main(int argc, char** argv) {
         if (memcmp(got, want, 32)) { printf("sqr mismatch %d\n", it); return 1; }
     }
     if (check_perm<5>(300) || check_perm<3>(100) || check_perm<9>(60)) return 1;
-    if (check_coop(80)) return 1;
+    if (check_coop<8>(80)) return 1;
+    if (check_coop<32>(60)) return 1;
     printf("host emulation OK\n");
     return 0;
 }

@@ -518,18 +518,21 @@ def test_merkle_tree_single_leaf_and_errors(cuda_strategy, oracle):
         cuda_strategy.merkle_root_ragged(np.empty((0, 4), dtype=np.uint64))
 
 
-# ---- cooperative small-batch kernels (coop.cuh): one state per 8 lanes ------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 63, 64, 65, 1000, 4735, 4736])
-def test_coop_perm_bit_identical(oracle, n):
-    """Batches at or below the cooperative threshold run perm_batch_coop_kernel; same bits as the oracle and as
-    the one-thread-per-state kernel (threshold 0)."""
+# ---- cooperative small-batch kernels (coop.cuh): one state per 8 lanes, or per warp -------------------------
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 63, 64, 65, 1000, 4735, 4736])
+def test_coop_perm_bit_identical(oracle, n, wide):
+    """Batches at or below the cooperative threshold run perm_batch_coop_kernel<8> (or <32>, a warp per state, below
+    the wide threshold); same bits as the oracle and as the one-thread-per-state kernel (threshold 0)."""
     import torch
     from hades252_b200 import CudaStrategy
     s = oracle.gen_elems(1234 + n, 5 * n).reshape(n, 5, 4)
     want = oracle.perm_batch(s)
     with CudaStrategy([0]) as strat:
         assert strat.kernel_info("perm_coop")["local_bytes"] == 0
+        assert strat.kernel_info("perm_coop_wide")["local_bytes"] == 0
         strat.set_coop_threshold(1 << 20)
+        strat.set_coop_wide_threshold((1 << 20) if wide else 0)
         l0 = strat.launch_count
         d = torch.from_numpy(s.view(np.int64).copy()).cuda()
         strat.perm_batch_device(d.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
@@ -551,11 +554,13 @@ def test_coop_single_perm_and_edge_values(oracle, H):
     P = H.P
     vals = [0, 1, P - 1, P - 2, H.R, (1 << 255) % P, (1 << 64) - 1, P >> 1]
     with CudaStrategy([0]) as strat:
-        for k in range(len(vals)):
-            st = np.array([H.to_mont_limbs(vals[(k + j) % len(vals)]) for j in range(5)], dtype=np.uint64)
-            want = oracle.perm_batch(st[None])[0]
-            strat.perm(st)
-            assert np.array_equal(st, want)
+        for wide in (592, 0):  # the default (a warp per state for a lone permutation), then the 8-lane kernel
+            strat.set_coop_wide_threshold(wide)
+            for k in range(len(vals)):
+                st = np.array([H.to_mont_limbs(vals[(k + j) % len(vals)]) for j in range(5)], dtype=np.uint64)
+                want = oracle.perm_batch(st[None])[0]
+                strat.perm(st)
+                assert np.array_equal(st, want)
 
 
 @pytest.mark.parametrize("n", [4 ** 6, 3 * 4 ** 5 + 77, 13])
@@ -567,9 +572,11 @@ def test_coop_merkle_levels(oracle, n):
     want = oracle.merkle_tree(leaves)[-1]
     with CudaStrategy([0]) as strat:
         strat.set_coop_threshold(1 << 20)
-        assert np.array_equal(strat.merkle_root_ragged(leaves), want)
-        if n == 4 ** 6:
-            assert np.array_equal(strat.merkle_root(leaves), want)
+        for wide in (0, 592, 1 << 20):  # 8 lanes per node everywhere / a warp per node on the top levels / everywhere
+            strat.set_coop_wide_threshold(wide)
+            assert np.array_equal(strat.merkle_root_ragged(leaves), want)
+            if n == 4 ** 6:
+                assert np.array_equal(strat.merkle_root(leaves), want)
         strat.set_coop_threshold(0)
         assert np.array_equal(strat.merkle_root_ragged(leaves), want)
 
@@ -919,11 +926,12 @@ def test_kernel_choice_never_changes_the_bits(oracle):
     strat = CudaStrategy([0])
     try:
         @settings(max_examples=40, deadline=None)
-        @given(n=st.integers(1, 6000), thr=st.sampled_from([0, 1, 7, 8, 9, 4735, 4736, 4737, 6000]), first=st.integers(0, 100),
-               host=st.booleans())
-        def check(n, thr, first, host):
+        @given(n=st.integers(1, 6000), thr=st.sampled_from([0, 1, 7, 8, 9, 4735, 4736, 4737, 6000]),
+               wide=st.sampled_from([0, 1, 3, 4, 5, 592, 6000]), first=st.integers(0, 100), host=st.booleans())
+        def check(n, thr, wide, first, host):
             n = min(n, 6000 - first)
             strat.set_coop_threshold(thr)
+            strat.set_coop_wide_threshold(wide)
             s = pool[first:first + n].copy()
             if host:
                 strat.perm_batch(s)
