@@ -1,29 +1,33 @@
-// Cooperative (low-latency) Hades252 permutation: ONE width-5 state per group of 8 lanes.
+// Cooperative (low-latency) Hades252 permutation: ONE width-5 state per group of 8 lanes, or per warp.
 //
 // Why: the one-thread-per-state kernels are throughput kernels.  A lone warp needs ~270 us for its 74 200
 // dependent-ish limb products, so every batch below ~2^14 states -- a lone `Strategy::perm`
 // (src/strategies.rs:140), the top levels of a Merkle tree -- pays that floor.  Lanes of a warp are free when
-// the batch is small, so here a group of 8 lanes shares one state (BASELINE north_star: "one thread (or a
-// small cooperative group) per state").
+// the batch is small, so here a group of G lanes shares one state (BASELINE north_star: "one thread (or a
+// small cooperative group) per state"): G = 8 (kCoopLanes) up to a few thousand states, G = 32 (kCoopWide) for the
+// smallest batches.
 //
 // How: SIMT lanes must run the same instruction, so the work is cut into SLOTS of one Montgomery product
 // r = a*b/R per lane (fr.cuh dot_mont<1>, CIOS) with lane-dependent operands, glued by warp shuffles:
-//   * the state is REPLICATED in all 8 lanes of the group (canonical words), so operands are picked by lane
+//   * the state is REPLICATED in all lanes of the group (canonical words), so operands are picked by lane
 //     index and nothing has to be routed before a slot;
 //   * partial round (gauged canonical form, hades.cuh partial_round_ccf): the S-box chain x^2, x^4, x^5 runs
 //     on lane 0 in slots 0..2; the 8 products of the two dot products (c_q.w and alpha_q.w) ride along in the
-//     other lanes (7 in slot 0, 1 in slot 1); their sums are formed by xor-butterflies while lane 0 is still
-//     squaring, so only "+ x^5, canonicalise" is left after slot 2: 3 products deep instead of 840/112 = 7.5;
-//   * full round: x^5 of the 5 words on lanes 0..4 (3 slots), then the 20 (25 in the last, dense round)
-//     matrix products in 3 (4) slots, each row summed by a butterfly over 4 lanes;
+//     other lanes (G = 8: 7 in slot 0, 1 in slot 1; G = 32: all in slot 0, which makes slot 1 a pure squaring
+//     slot); their sums are formed by xor-butterflies and canonicalised while lane 0 is still multiplying, so only
+//     "+ x^5, two conditional subtractions" is left after slot 2: 3 products deep instead of 840/112 = 7.5;
+//   * full round: x^5 of the 5 words on lanes 0..4 (two squaring slots, one product slot), then the 20 (25 in the
+//     last, dense round) matrix products in 3 (4 + 1) slots with 8 lanes, in 1 (2) with a warp; each row is summed by
+//     a butterfly over 4 lanes;
 //   * every product is reduced on its own (Montgomery reduction is linear), sums are taken on the reduced
 //     9-limb values and canonicalised once per output word.
 // Same tables as the one-thread canonical-form kernel (CcfLayout<5>), same F_p values, canonical outputs:
-// bit-identical results.  Per permutation: 59*3 + 7*6 + 7 + 2 = 228 slots of 112 products.
+// bit-identical results.  Slots per permutation: 59*3 + 7*6 + 7 + 2 = 228 with 8 lanes, 59*3 + 7*4 + 5 + 1 = 211
+// with a warp (59 + 16 of them squarings).
 //
 // `T::tab(entry, limb)` must accept a lane-dependent entry (the kernels copy the table to shared memory).
-// Shuffles go through coop_shfl / coop_shfl_xor: warp shuffles of width 8 on the device; in the host
-// emulation build (tests/host_emul) eight threads exchange through a barrier.
+// Shuffles go through coop_shfl_n<G> / coop_shfl_xor_n<G>: warp shuffles of width G on the device; in the host
+// emulation build (tests/host_emul) G threads exchange through a barrier.
 #pragma once
 #include "hades.cuh"
 

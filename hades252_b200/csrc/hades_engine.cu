@@ -38,10 +38,10 @@ constexpr int kNumBuf = 4;                       // chunk buffers (and streams) 
 constexpr size_t kChunkBytes = (size_t)96 << 20;  // target bytes per pipeline chunk
 // Batches / Merkle levels up to this many states run the cooperative 8-lanes-per-state kernels (coop.cuh): below it
 // the one-thread-per-state kernel is latency-bound (one warp per scheduler, ~270 us whatever the size).
-// Measured (profiles/r02_latency_small_batches.txt): 127 us up to 2368 states (one 16-state block per SM), 178 us up to
-// 4736, 333 us at 8192 -- against 269 us for the one-thread kernel at any size up to 16 384.
+// Measured (profiles/r02_latency_small_batches.txt): 111-113 us up to 2368 states (one 16-state block per SM), 168 us up to
+// 4736, 314 us at 8192 -- against 270 us for the one-thread kernel at any size up to 16 384.
 constexpr int kDefaultCoopMax = 4736;
-// ... and up to this many the warp-per-state version (one block of four states per SM): 97 us instead of 111 us for a
+// ... and up to this many the warp-per-state version (one block of four states per SM): 98.6 us instead of 111 us for a
 // lone permutation, slower than the 8-lane kernel beyond one block per SM
 constexpr int kDefaultCoopWideMax = 592;
 

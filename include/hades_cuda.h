@@ -212,7 +212,7 @@ int hades_kernel_info(hades_ctx* ctx, const char* kernel, int* regs_per_thread, 
  * 128-thread blocks (the default; see hades252_b200/csrc/width_ops.hpp). */
 int hades_set_variant(hades_ctx* ctx, int algo, int regs);  /* HADES_ERR_INVALID_ARG for a shape not built for the width */
 /* Small-batch path: batches, Merkle levels and sponge calls of at most `max_states` states / messages run the cooperative kernels --
- * one state per group of 8 lanes, 2.1x lower latency (125 us) than the one-thread-per-state kernel, which is
+ * one state per group of 8 lanes, 2.4x lower latency (111 us) than the one-thread-per-state kernel, which is
  * latency-bound below ~2^14 states (a lone `Strategy::perm`, strategies.rs:140, is a batch of one).  Width 5,
  * algo 2 only; 0 disables; default 4736 (two 16-state blocks per SM).  Results are bit-identical either way. */
 int hades_set_coop_threshold(hades_ctx* ctx, size_t max_states);
