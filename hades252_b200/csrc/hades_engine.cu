@@ -44,6 +44,10 @@ constexpr int kDefaultCoopMax = 4736;
 // ... and up to this many the warp-per-state version (one block of four states per SM): 98.6 us instead of 111 us for a
 // lone permutation, slower than the 8-lane kernel beyond one block per SM
 constexpr int kDefaultCoopWideMax = 592;
+// Host batches of at most this many bytes on a single-device context (a lone `Strategy::perm` is 160 B) skip the copy
+// engines: the states are memcpy'd into a mapped page-locked buffer and the kernel reads and writes that buffer over
+// PCIe.  Two cudaMemcpyAsync calls of ~10 us each are a quarter of the 99 us kernel.
+constexpr size_t kTinyBytes = 16 << 10;
 
 struct DeviceState {
     int ordinal = 0;
@@ -56,6 +60,8 @@ struct DeviceState {
     cudaEvent_t done[kNumBuf] = {};      // chunk b's D2H has landed in bounce[b]
     uint64_t* work = nullptr;            // persistent scratch of the Merkle / sponge host paths (grow-only)
     size_t work_bytes = 0;
+    uint64_t* tiny = nullptr;            // mapped page-locked buffer of the tiny-batch host path (kTinyBytes) ...
+    uint64_t* tiny_dev = nullptr;        // ... and its device alias: the kernel works on it in place, no copies
     ncclComm_t comm = nullptr;           // rank of this device in the context's communicator (n_dev > 1)
 };
 
@@ -263,6 +269,20 @@ int ensure_bounce(hades_ctx* ctx, DeviceState& d, size_t bytes) {
     d.bounce_bytes = 0;
     for (int b = 0; b < kNumBuf; b++) CUDA_TRY(ctx, cudaHostAlloc(&d.bounce[b], bytes, cudaHostAllocPortable));
     d.bounce_bytes = bytes;
+    return HADES_OK;
+}
+int ensure_tiny(hades_ctx* ctx, DeviceState& d) {
+    if (d.tiny) return HADES_OK;
+    void* h = nullptr;
+    CUDA_TRY(ctx, cudaHostAlloc(&h, kTinyBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    void* dp = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dp, h, 0);
+    if (e != cudaSuccess) {
+        cudaFreeHost(h);
+        CUDA_TRY(ctx, e);
+    }
+    d.tiny = static_cast<uint64_t*>(h);
+    d.tiny_dev = static_cast<uint64_t*>(dp);
     return HADES_OK;
 }
 int ensure_work(hades_ctx* ctx, DeviceState& d, size_t bytes) {
@@ -512,6 +532,7 @@ void hades_destroy(hades_ctx* ctx) {
             if (d.streams[b]) cudaStreamDestroy(d.streams[b]);
         }
         if (d.work) cudaFree(d.work);
+        if (d.tiny) cudaFreeHost(d.tiny);
         if (d.generic_tables) cudaFree(d.generic_tables);
     }
     delete ctx;
@@ -540,6 +561,20 @@ int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n) {
     DeviceGuard guard;
     const size_t state_bytes = (size_t)ctx->width * 32;
     const size_t G = ctx->devs.size();
+    if (G == 1 && n * state_bytes <= kTinyBytes && !ctx->probe && !ctx->force_bounce && !ctx->force_direct) {
+        // tiny batch (a lone `Strategy::perm`, src/strategies.rs:140): in place on a mapped page-locked buffer
+        DeviceState& d = ctx->devs[0];
+        CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+        int r = ensure_tiny(ctx, d);
+        if (r) return r;
+        memcpy(d.tiny, host_states, n * state_bytes);
+        r = launch_perm_w(ctx, d.tiny_dev, n, d.streams[0], &d);
+        if (r) return r;
+        CUDA_TRY(ctx, cudaStreamSynchronize(d.streams[0]));
+        memcpy(host_states, d.tiny, n * state_bytes);
+        ctx->last_host_path = "tiny batch: the kernel works in place on a mapped page-locked buffer (no copy engines)";
+        return HADES_OK;
+    }
     size_t chunk_states = std::max<size_t>(kPermThreads, kChunkBytes / state_bytes / kPermThreads * kPermThreads);
     // Medium batches (at least kMinSplitBytes per chunk) are split into kNumBuf chunks so that H2D, kernel and D2H --
     // and, for pageable memory, the staging copies -- overlap.  Smaller batches go as ONE chunk: a launch is one

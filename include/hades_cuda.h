@@ -76,7 +76,9 @@ int hades_device_count(const hades_ctx* ctx);
  * HOST pointer.  Sharded in contiguous ranges over the context's devices, each range streamed in
  * chunks (H2D / kernel / D2H overlapped on separate streams).  Synchronous: on return the host
  * buffer holds the outputs.  Pinned (page-locked) host memory makes the copies asynchronous; see
- * hades_host_register.  Replaces: a loop of `ScalarStrategy::perm` (strategies.rs:140).
+ * hades_host_register.  A batch of at most 16 KB on a single-device context (a lone `Strategy::perm` is
+ * 160 bytes) skips the copy engines: it is staged in a mapped page-locked buffer the kernel works on in place.
+ * Replaces: a loop of `ScalarStrategy::perm` (strategies.rs:140).
  */
 int hades_perm_batch(hades_ctx* ctx, uint64_t* host_states, size_t n);
 
