@@ -464,18 +464,21 @@ merkle_level_coop_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, 
 // Sponge for few messages (a lone hash is the commonest call a Poseidon user makes): one message per 8-lane group,
 // no length bucketing; the four groups of a warp run the warp's maximum block count (all 32 lanes must reach every
 // shuffle), a group whose message ended earlier keeps permuting a dead state and has already captured its digest.
+template <int G>
 __global__ void __launch_bounds__(kCoopBlock)
 sponge_coop_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__ offsets, uint4* __restrict__ out, size_t n_msgs,
                    const SpongeTag tag) {
     coop_stage_table();
-    const int lane = threadIdx.x & (kCoopLanes - 1);
-    const size_t g = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const int lane = threadIdx.x & (G - 1);
+    const size_t g = (size_t)blockIdx.x * (kCoopBlock / G) + (threadIdx.x / G);
     const bool live = g < n_msgs;
     uint64_t b = live ? offsets[g] : 0, e = live ? offsets[g + 1] : 0;
     const unsigned my_blocks = live ? (unsigned)((e - b) / 4 + 1) : 0u;
     unsigned trips = my_blocks;
-    trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 8));
-    trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 16));
+    if constexpr (G < 32) {  // several groups per warp: all of them run the warp's maximum
+        trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 8));
+        trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 16));
+    }
     Fr s[5], digest;
 #pragma unroll
     for (int j = 0; j < 5; j++) fr_set_zero(s[j]);
@@ -500,19 +503,20 @@ sponge_coop_kernel(const uint4* __restrict__ elems, const uint64_t* __restrict__
             }
             if (add) fr_add(s[1 + k], s[1 + k], x);
         }
-        hades_perm_coop<CoopTab>(s, lane);
+        hades_perm_coop<CoopTab, G>(s, lane);
         if (trip + 1 == my_blocks) digest = s[1];
     }
     if (live && lane == 0) fr_store(out + g * 2, digest);
 }
 
 // Verification of few openings (a lone verify is a chain of `levels` permutations): one opening per 8-lane group.
+template <int G>
 __global__ void __launch_bounds__(kCoopBlock)
 merkle_verify_coop_kernel(const uint4* __restrict__ leaves, const uint64_t* __restrict__ index, size_t n_open, size_t n_leaves,
                           int levels, const uint4* __restrict__ branch, const uint4* __restrict__ root, uint32_t* __restrict__ ok) {
     coop_stage_table();
-    const int lane = threadIdx.x & (kCoopLanes - 1);
-    const size_t o = (size_t)blockIdx.x * kCoopStatesPerBlock + (threadIdx.x / kCoopLanes);
+    const int lane = threadIdx.x & (G - 1);
+    const size_t o = (size_t)blockIdx.x * (kCoopBlock / G) + (threadIdx.x / G);
     const bool live = o < n_open;
     size_t i = live ? index[o] : 0, m = n_leaves;
     bool good = live && i < n_leaves;
@@ -533,7 +537,7 @@ merkle_verify_coop_kernel(const uint4* __restrict__ leaves, const uint64_t* __re
             if (j == pos) good &= fr_equal(s[1 + j], node);
             if (j >= k) good &= fr_is_zero(s[1 + j]);
         }
-        hades_perm_coop<CoopTab>(s, lane);
+        hades_perm_coop<CoopTab, G>(s, lane);
         node = s[1];
         i >>= 2;
         m = (m + 3) / 4;
@@ -651,9 +655,16 @@ cudaError_t launch_merkle_verify(Variant v, const uint64_t* d_leaves, const uint
                                  const uint64_t* d_branch, const uint64_t* d_root, uint32_t* d_ok, cudaStream_t s) {
     if (n_open == 0) return cudaSuccess;
 #if HADES_ALGO == 2
-    if (n_open <= (size_t)v.coop_max) {  // few openings: 8 lanes per opening (latency kernel)
+    if (n_open <= (size_t)v.coop_max) {  // few openings: 8 lanes, or a warp, per opening (latency kernels)
+        if (n_open <= (size_t)v.coop_wide_max) {
+            constexpr int kPer = kCoopBlock / kCoopWide;
+            merkle_verify_coop_kernel<kCoopWide><<<(unsigned)((n_open + kPer - 1) / kPer), kCoopBlock, kCoopSmemBytes, s>>>(
+                reinterpret_cast<const uint4*>(d_leaves), d_index, n_open, n_leaves, levels, reinterpret_cast<const uint4*>(d_branch),
+                reinterpret_cast<const uint4*>(d_root), d_ok);
+            return cudaGetLastError();
+        }
         const unsigned cblocks = (unsigned)((n_open + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
-        merkle_verify_coop_kernel<<<cblocks, kCoopBlock, kCoopSmemBytes, s>>>(
+        merkle_verify_coop_kernel<kCoopLanes><<<cblocks, kCoopBlock, kCoopSmemBytes, s>>>(
             reinterpret_cast<const uint4*>(d_leaves), d_index, n_open, n_leaves, levels, reinterpret_cast<const uint4*>(d_branch),
             reinterpret_cast<const uint4*>(d_root), d_ok);
         return cudaGetLastError();
@@ -672,10 +683,16 @@ cudaError_t launch_sponge(Variant v, const uint64_t* d_elems, const uint64_t* d_
                           uint64_t* d_out, size_t n_threads, SpongeTag tag, cudaStream_t s) {
     if (n_threads == 0) return cudaSuccess;
 #if HADES_ALGO == 2
-    if (n_threads <= (size_t)v.coop_max) {  // few messages: 8 lanes per message (latency kernel), no bucketing needed
+    if (n_threads <= (size_t)v.coop_max) {  // few messages: 8 lanes, or a warp, per message (latency kernels), no bucketing needed
+        if (n_threads <= (size_t)v.coop_wide_max) {
+            constexpr int kPer = kCoopBlock / kCoopWide;
+            sponge_coop_kernel<kCoopWide><<<(unsigned)((n_threads + kPer - 1) / kPer), kCoopBlock, kCoopSmemBytes, s>>>(
+                reinterpret_cast<const uint4*>(d_elems), d_offsets, reinterpret_cast<uint4*>(d_out), n_threads, tag);
+            return cudaGetLastError();
+        }
         const unsigned blocks = (unsigned)((n_threads + kCoopStatesPerBlock - 1) / kCoopStatesPerBlock);
-        sponge_coop_kernel<<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(reinterpret_cast<const uint4*>(d_elems), d_offsets,
-                                                                      reinterpret_cast<uint4*>(d_out), n_threads, tag);
+        sponge_coop_kernel<kCoopLanes><<<blocks, kCoopBlock, kCoopSmemBytes, s>>>(
+            reinterpret_cast<const uint4*>(d_elems), d_offsets, reinterpret_cast<uint4*>(d_out), n_threads, tag);
         return cudaGetLastError();
     }
 #endif
@@ -710,7 +727,8 @@ cudaError_t func_attributes(const char* kernel, Variant v, cudaFuncAttributes* o
     if (!strcmp(kernel, "merkle_coop")) return cudaFuncGetAttributes(out, merkle_level_coop_kernel<kCoopLanes>);
     if (!strcmp(kernel, "perm_coop_wide")) return cudaFuncGetAttributes(out, perm_batch_coop_kernel<kCoopWide>);
     if (!strcmp(kernel, "merkle_coop_wide")) return cudaFuncGetAttributes(out, merkle_level_coop_kernel<kCoopWide>);
-    if (!strcmp(kernel, "sponge_coop")) return cudaFuncGetAttributes(out, sponge_coop_kernel);
+    if (!strcmp(kernel, "sponge_coop")) return cudaFuncGetAttributes(out, sponge_coop_kernel<kCoopLanes>);
+    if (!strcmp(kernel, "sponge_coop_wide")) return cudaFuncGetAttributes(out, sponge_coop_kernel<kCoopWide>);
 #endif
 #if HADES_ALGO >= 1
     if (!strcmp(kernel, "perm") && v.regs == 4) return cudaFuncGetAttributes(out, perm_batch_lockstep_kernel<256, 2>);

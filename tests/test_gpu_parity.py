@@ -821,7 +821,13 @@ def test_merkle_open_verify_roundtrip_and_tampering(cuda_strategy, oracle, H, n)
     cuda_strategy.merkle_open_device(d_leaves.data_ptr(), d_tree.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), sp)
     cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), d_root.data_ptr(), d_ok.data_ptr(), sp)
     torch.cuda.synchronize()
-    assert d_ok.cpu().numpy().tolist() == [1] * k              # every genuine opening verifies (cooperative kernel: k <= 4736)
+    assert d_ok.cpu().numpy().tolist() == [1] * k              # every genuine opening verifies (cooperative kernels: k <= 4736)
+    cuda_strategy.set_coop_wide_threshold(0)                   # ... on the 8-lane kernel alone
+    d_ok.fill_(7)
+    cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), d_root.data_ptr(), d_ok.data_ptr(), sp)
+    torch.cuda.synchronize()
+    cuda_strategy.set_coop_wide_threshold(592)
+    assert d_ok.cpu().numpy().tolist() == [1] * k
     cuda_strategy.set_coop_threshold(0)                        # ... and on the one-thread kernel
     d_ok.fill_(7)
     cuda_strategy.merkle_verify_device(d_leaves.data_ptr(), n, d_idx.data_ptr(), k, d_branch.data_ptr(), d_root.data_ptr(), d_ok.data_ptr(), sp)
@@ -907,10 +913,13 @@ def test_coop_sponge_few_messages(oracle):
         want_tag = oracle.sponge_batch(elems, offsets, domain_tag=tag)
         with CudaStrategy([0]) as s:
             assert s.kernel_info("sponge_coop")["local_bytes"] == 0
-            l0 = s.launch_count
-            assert np.array_equal(s.sponge_batch(elems, offsets), want)
-            assert s.launch_count == l0 + 1
-            assert np.array_equal(s.sponge_batch(elems, offsets, domain_tag=tag), want_tag)
+            assert s.kernel_info("sponge_coop_wide")["local_bytes"] == 0
+            for wide in (592, 0, 1 << 20):  # default (a warp per message up to 592 messages) / 8 lanes only / a warp always
+                s.set_coop_wide_threshold(wide)
+                l0 = s.launch_count
+                assert np.array_equal(s.sponge_batch(elems, offsets), want)
+                assert s.launch_count == l0 + 1
+                assert np.array_equal(s.sponge_batch(elems, offsets, domain_tag=tag), want_tag)
             s.set_coop_threshold(0)
             assert np.array_equal(s.sponge_batch(elems, offsets), want)
 

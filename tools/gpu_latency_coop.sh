@@ -23,3 +23,21 @@ for n in (1, 8, 64, 512, 592, 593, 1024, 1184, 2048, 2368, 4096, 4736, 8192, 163
     s.set_coop_threshold(0); o = t(n)
     print(f"n={n:6d}  warp per state {w:8.1f} us   8 lanes per state {c:8.1f} us   one thread per state {o:8.1f} us")
 PY
+python - <<'PY'
+# a lone sponge hash (9 elements = 3 permutations) through the host call, per kernel choice
+import time
+import numpy as np
+from hades252_b200 import CudaStrategy
+from oracle import cpu_oracle as C
+s = CudaStrategy([0])
+elems = C.gen_elems(5, 9); offsets = np.array([0, 9], dtype=np.uint64)
+def t(reps=200):
+    s.sponge_batch(elems, offsets)
+    t0 = time.perf_counter()
+    for _ in range(reps): s.sponge_batch(elems, offsets)
+    return (time.perf_counter() - t0) / reps * 1e6
+s.set_coop_threshold(4736); s.set_coop_wide_threshold(592); w = t()
+s.set_coop_wide_threshold(0); c = t()
+s.set_coop_threshold(0); o = t()
+print(f"lone sponge hash of 9 elements (3 permutations), host call: warp per message {w:7.1f} us   8 lanes {c:7.1f} us   one thread {o:7.1f} us")
+PY
