@@ -218,7 +218,8 @@ int hades_set_variant(hades_ctx* ctx, int algo, int regs);  /* HADES_ERR_INVALID
  * latency-bound below ~2^14 states (a lone `Strategy::perm`, strategies.rs:140, is a batch of one).  Width 5,
  * algo 2 only; 0 disables; default 4736 (two 16-state blocks per SM).  Results are bit-identical either way. */
 int hades_set_coop_threshold(hades_ctx* ctx, size_t max_states);
-/* Batches and Merkle levels of at most `max_states` states (and within the threshold above) give each state a whole
+/* Batches, Merkle levels, sponge calls and opening verifications of at most `max_states` states / messages / openings
+ * (and within the threshold above) give each state a whole
  * warp instead of 8 lanes: all matrix products of a full round and all dot products of a partial round fit one slot
  * each.  Lowest latency for a lone permutation, a quarter of the capacity per block; default 592 (one block of four
  * states per SM), 0 disables.  Bit-identical results. */
