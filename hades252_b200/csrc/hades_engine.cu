@@ -1095,6 +1095,27 @@ static int sponge_host(hades_ctx* ctx, const uint64_t* elems, const uint64_t* of
     for (size_t m = 0; m < n_msgs; m++)
         if (offsets[m + 1] < offsets[m]) return fail(ctx, HADES_ERR_INVALID_ARG, "offsets must be non-decreasing");
     if (offsets[n_msgs] > offsets[0] && !elems) return fail(ctx, HADES_ERR_INVALID_ARG, "null elems pointer");
+    {   // tiny call (a lone hash): the one-launch cooperative kernel works on a mapped page-locked buffer, no copy engines
+        const uint64_t e0 = offsets[0], ne = offsets[n_msgs] - e0;
+        const size_t elems_u64 = (size_t)std::max<uint64_t>(ne, 1) * 4, out_u64 = n_msgs * 4;
+        if (ctx->variant.algo == 2 && n_msgs <= (size_t)ctx->variant.coop_max && ne <= kTinyBytes / 32 &&
+            (elems_u64 + out_u64 + n_msgs + 1) * 8 <= kTinyBytes) {
+            DeviceGuard guard;
+            DeviceState& d = ctx->devs[0];
+            CUDA_TRY(ctx, cudaSetDevice(d.ordinal));
+            int r = ensure_tiny(ctx, d);
+            if (r) return r;
+            if (ne) memcpy(d.tiny, elems + e0 * 4, ne * 32);
+            memcpy(d.tiny + elems_u64 + out_u64, offsets, (n_msgs + 1) * 8);
+            // offsets stay absolute: bias the element base pointer by the first offset
+            r = sponge_dev(ctx, 0, d.tiny_dev - e0 * 4, d.tiny_dev + elems_u64 + out_u64, n_msgs, d.tiny_dev + elems_u64, tag,
+                           d.streams[0]);
+            if (r) return r;
+            CUDA_TRY(ctx, cudaStreamSynchronize(d.streams[0]));
+            memcpy(out, d.tiny + elems_u64, n_msgs * 32);
+            return HADES_OK;
+        }
+    }
     // contiguous message ranges per device, balanced by permutation count (floor(len/4) + 1 each)
     const size_t G = std::min<size_t>(ctx->devs.size(), std::max<size_t>(1, n_msgs / 4096));
     std::vector<size_t> bound(G + 1, n_msgs);
